@@ -1,0 +1,114 @@
+/*
+ * zfp_b200_backend.h - the C-ABI boundary between zfp's host dispatch and the sm_100a kernels.
+ *
+ * Plain C, no CUDA or torch types in any signature (a cudaStream_t travels as void*).
+ *
+ * (1) Drop-in symbols.  The reference's CUDA shims call exactly two functions
+ *         size_t cuda_compress(zfp_stream*, const zfp_field*);     src/cuda_zfp/cuZFP.h:9
+ *         void   cuda_decompress(zfp_stream*, zfp_field*);          src/cuda_zfp/cuZFP.h:10
+ *     from src/template/cudacompress.c:5-34 and cudadecompress.c:5-34.  libzfp_b200 exports both
+ *     with the same signatures and the same post-conditions on the host `bitstream`
+ *     (src/cuda_zfp/cuZFP.cu:406-411, 486-490), so a reference libzfp built with
+ *     -DZFP_WITH_CUDA links against this library instead of src/cuda_zfp.
+ *     Unlike the code they replace they accept every mode, 1-4 D, a non-zero stream offset.
+ *
+ * (2) Raw entry points on plain pointers and sizes, used by bindings (ctypes/cgo/JNI style) and
+ *     by the multi-GPU slab driver: one call = one slab.
+ *
+ * (3) The block-offset index that makes variable-rate streams decodable in parallel
+ *     (the zfp format itself stores none: docs/source/execution.rst:292-300).
+ */
+#ifndef ZFP_B200_BACKEND_H
+#define ZFP_B200_BACKEND_H
+
+#include "zfp_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- (1) drop-in replacements for src/cuda_zfp/cuZFP.h:9-10 ------------------------------- */
+size_t cuda_compress(zfp_stream* stream, const zfp_field* field);
+void cuda_decompress(zfp_stream* stream, zfp_field* field);
+/* the same two operations with an explicit status: bytes from the start of the stream, 0 = failed */
+size_t zfp_b200_compress_stream(zfp_stream* stream, const zfp_field* field);
+size_t zfp_b200_decompress_stream(zfp_stream* stream, zfp_field* field);
+
+/* ---- execution parameters hung off zfp_stream.exec.params for zfp_exec_cuda ----------------- */
+typedef struct zfp_b200_index zfp_b200_index; /* opaque; device-resident */
+
+typedef struct {
+  uint64 magic;          /* ZFP_B200_PARAMS_MAGIC; anything else is ignored */
+  void* cuda_stream;     /* cudaStream_t to launch on; NULL = legacy default stream */
+  int device_only_sync;  /* 0: calls return after the work is complete (reference semantics);
+                            1: fixed-rate calls return as soon as the work is enqueued */
+  zfp_b200_index* index; /* produced by the last variable-rate compress on this zfp_stream, consumed
+                            by decompress; owned by the zfp_stream */
+} zfp_exec_params_cuda;
+
+#define ZFP_B200_PARAMS_MAGIC 0x7a66704232303021ull
+
+/* get (creating on demand) the CUDA execution parameters of a stream whose policy is
+ * zfp_exec_cuda; NULL otherwise */
+zfp_exec_params_cuda* zfp_stream_cuda_params(zfp_stream* zfp);
+
+/* ---- (2) raw slab entry points ----------------------------------------------------------------- */
+typedef struct {
+  int type;        /* zfp_type */
+  uint dims;       /* 1..4 */
+  size_t n[4];     /* nx, ny, nz, nw */
+  ptrdiff_t s[4];  /* element strides, 0 = contiguous default */
+  uint minbits, maxbits, maxprec;
+  int minexp;
+} zfp_b200_desc;
+
+enum {
+  ZFP_B200_OK = 0,
+  ZFP_B200_EINVAL = 1,     /* bad type / dims / parameters */
+  ZFP_B200_ECUDA = 2,      /* a CUDA call failed; see zfp_b200_last_error() */
+  ZFP_B200_ENOINDEX = 3    /* variable-rate decode of a stream without a usable index */
+};
+
+/* Encode the field at device pointer d_data into device words d_words starting at bit
+ * start_bit (bits below start_bit in the first word are preserved).  *end_bit receives the bit
+ * offset one past the last block; words beyond it up to the next word boundary are zero, as after
+ * stream_flush.  For variable-rate parameters, if index != NULL it is filled with the block
+ * lengths.  All work is enqueued on cuda_stream; the call synchronises that stream only when it
+ * must read a size back (variable rate). */
+int zfp_b200_encode(const zfp_b200_desc* desc, const void* d_data, void* d_words, uint64 start_bit,
+                    uint64* end_bit, zfp_b200_index* index, void* cuda_stream);
+
+/* Decode; mirror of the above.  index may be NULL for fixed-rate parameters.  For variable-rate
+ * parameters a NULL index makes the backend rebuild one by scanning the stream (slow, sequential
+ * in the stream order by the nature of the format). */
+int zfp_b200_decode(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
+                    uint64* end_bit, const zfp_b200_index* index, void* cuda_stream);
+
+/* 1 if the parameters make every block the same size (minbits == maxbits) */
+int zfp_b200_is_fixed_rate(const zfp_b200_desc* desc);
+/* number of 4^d blocks in the field */
+size_t zfp_b200_blocks(const zfp_b200_desc* desc);
+/* capacity in bytes a caller must provide for d_words (zfp_stream_maximum_size formula,
+ * src/zfp.c:711-742, plus the words covering start_bit) */
+size_t zfp_b200_capacity(const zfp_b200_desc* desc, uint64 start_bit);
+
+/* ---- (3) block-offset index -------------------------------------------------------------------- */
+zfp_b200_index* zfp_b200_index_create(void);
+void zfp_b200_index_destroy(zfp_b200_index* index);
+size_t zfp_b200_index_blocks(const zfp_b200_index* index);
+/* serialised form: 16-bit coded length per block, block order = stream order */
+size_t zfp_b200_index_export(const zfp_b200_index* index, uint16_t* host_lengths, size_t capacity);
+int zfp_b200_index_import(zfp_b200_index* index, const uint16_t* host_lengths, size_t blocks);
+
+/* ---- diagnostics --------------------------------------------------------------------------------- */
+const char* zfp_b200_last_error(void);
+/* number of kernels this library launched since load (bench.py's gpu_launches counter) */
+uint64 zfp_b200_launch_count(void);
+/* release cached device scratch */
+void zfp_b200_release_scratch(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ZFP_B200_BACKEND_H */

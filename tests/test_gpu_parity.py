@@ -1,0 +1,174 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle.
+
+Every comparison is bit-exact (streams byte for byte, decompressed arrays bit for bit); the
+only floating-point tolerance that appears is the user's own fixed-accuracy bound.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, MODE_ID, analytic_field, make_field, ref_key, ref_mode_cases, ref_table, sha
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64, np.int32, np.int64]
+
+
+@pytest.fixture(scope="module")
+def zb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import zfp_b200
+    zfp_b200.load_library(build_if_missing=False)
+    return zfp_b200
+
+
+def _mode(c):
+    mode = dict(c["mode"])
+    if "expert" in mode:
+        mode["expert"] = tuple(mode["expert"])
+    return mode
+
+
+def test_kat_vectors_host_pointers(zb):
+    """1728 known-answer vectors made by the unmodified reference (tests/golden/make_kat.py):
+    1-4 D, four types, partial blocks, all modes; host arrays staged by the backend."""
+    with open(os.path.join(GOLDEN, "kat.json")) as f:
+        kat = json.load(f)
+    bad = []
+    for c in kat:
+        a = make_field(tuple(c["shape"]), c["dtype"], c["seed"], c["kind"])
+        mode = _mode(c)
+        variable = "rate" not in mode
+        res = zb.compress_numpy(a, want_index=variable, **mode)
+        words, nbytes = res[0], res[1]
+        ok = nbytes == c["nbytes"] and sha(words) == c["stream"]
+        if ok:
+            back, used = zb.decompress_numpy(words, a.shape, a.dtype, index=res[2] if variable else None, **mode)
+            ok = used == nbytes and sha(back) == c["decoded"]
+        if not ok:
+            bad.append({k: c[k] for k in ("shape", "dtype", "kind", "mode")})
+    assert not bad, "%d of %d vectors differ, first: %r" % (len(bad), len(kat), bad[:5])
+
+
+@pytest.mark.parametrize("dims", [1, 2, 3, 4])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reference_golden_tables_device(zb, port, reftest, dtype, dims):
+    """The reference's own end-to-end checksum tables (the ones its CUDA tests use,
+    tests/src/endtoend/cudaExecBase.c:107-111), device-resident input and stream."""
+    import torch
+    a = reftest.smooth_field(dtype, dims)
+    side = a.shape[0]
+    table = ref_table(dtype, dims)
+    x = torch.from_numpy(a).cuda()
+    for name, p, mode in ref_mode_cases(dtype):
+        c = zb.compress(x, **mode)
+        words = c.to_numpy()
+        assert port.hash_stream(words) == table[ref_key(1, MODE_ID[name], p, side, dims)], (name, p)
+        back = zb.decompress(c).cpu().numpy()
+        if name == "reversible":
+            assert back.tobytes() == a.tobytes()
+        else:
+            assert port.hash_array(back) == table[ref_key(2, MODE_ID[name], p, side, dims)], (name, p)
+            if name == "accuracy":
+                assert np.max(np.abs(back.astype(np.float64) - a.astype(np.float64))) <= mode["accuracy"]
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (96, 100, 128)), (np.float32, (128, 96, 100)),
+                                         (np.float32, (1000, 1028)), (np.float64, (515, 300)),
+                                         (np.float64, (20, 24, 28, 32)), (np.int32, (64, 64, 68)),
+                                         (np.float64, (100003,))])
+def test_device_vs_oracle_analytic(zb, port, dtype, shape):
+    """Smooth analytic fields, device resident, against the oracle on the same bytes."""
+    import torch
+    a = analytic_field(shape, dtype)
+    x = torch.from_numpy(a).cuda()
+    modes = [{"rate": 4}, {"rate": 8}, {"rate": 16}, {"precision": 32}, {"reversible": True}]
+    if np.dtype(dtype).kind == "f":
+        modes += [{"accuracy": 1e-6}]
+    for mode in modes:
+        c = zb.compress(x, **mode)
+        want = port.compress(a, **mode)
+        got = c.to_numpy()
+        assert got.nbytes == want.nbytes, (mode, got.nbytes, want.nbytes)
+        assert got.tobytes() == want.tobytes(), mode
+        back = zb.decompress(c).cpu().numpy()
+        assert back.tobytes() == port.decompress(want, a.shape, a.dtype, **mode).tobytes(), mode
+        if "accuracy" in mode:
+            assert np.max(np.abs(back.astype(np.float64) - a.astype(np.float64))) <= mode["accuracy"]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_strides_and_stream_offsets(zb, port, dtype):
+    """Negative, gapped and permuted strides; payload starting mid-word after a header."""
+    import torch
+    rng = np.random.default_rng(3)
+    for dims, n in [(1, [37, 0, 0, 0]), (2, [13, 10, 0, 0]), (3, [9, 6, 7, 0]), (4, [5, 6, 4, 7])]:
+        total = int(np.prod([v for v in n if v]))
+        base = make_field((3 * total + 11,), dtype, seed=dims, kind="smooth")
+        shape = tuple(reversed([v for v in n if v]))
+        layouts = []
+        s, acc = [0] * 4, 1
+        for d in range(dims):
+            s[d] = -acc
+            acc *= n[d]
+        layouts.append((s, total - 1 + 5))
+        s, acc = [0] * 4, 2
+        for d in range(dims):
+            s[d] = acc
+            acc *= n[d]
+        layouts.append((s, 3))
+        if dims > 1:
+            s, acc = [0] * 4, 1
+            for d in reversed(range(dims)):
+                s[d] = acc
+                acc *= n[d]
+            layouts.append((s, 0))
+        xb = torch.from_numpy(base).cuda()
+        for s, off in layouts:
+            tstrides = tuple(reversed(s[:dims]))
+            x = torch.as_strided(xb, shape, tstrides, off) if min(tstrides) > 0 else None
+            for mode in ({"rate": 6}, {"precision": 11}, {"reversible": True}):
+                for start in (0, 96, 37):
+                    prefix = rng.integers(0, 2 ** 63, size=2, dtype=np.uint64)
+                    prefix[start // 64:] = 0
+                    if start % 64:
+                        prefix[start // 64] = rng.integers(0, 2 ** 63, dtype=np.uint64) & np.uint64((1 << (start % 64)) - 1)
+                    want, end = port.compress_raw(base, off, dtype, n, s, mode, start_bit=start, prefix_words=prefix)
+                    # host view with the same strides (numpy handles negative strides)
+                    view = np.lib.stride_tricks.as_strided(base[off:], shape, tuple(v * base.itemsize for v in tstrides))
+                    got, nbytes = zb.compress_numpy(view, start_bit=start, prefix_words=prefix, **mode)
+                    assert nbytes == 8 * ((end + 63) // 64)
+                    assert got.tobytes() == want.tobytes(), (dims, s, mode, start)
+                    if x is not None:
+                        out = torch.zeros(zb.max_stream_words(shape, x.dtype, mode, start), dtype=torch.int64, device="cuda")
+                        out[:2] = torch.from_numpy(prefix.view(np.int64)).cuda()
+                        c = zb.compress(x, out=out, start_bit=start, **mode)
+                        assert c.to_numpy().tobytes() == want.tobytes(), (dims, s, mode, start, "device")
+                        y = torch.zeros_like(xb)
+                        yv = torch.as_strided(y, shape, tstrides, off)
+                        zb.decompress(c, out=yv)
+                        ref_out = np.zeros_like(base)
+                        port.decompress_raw(want, ref_out, off, dtype, n, s, mode, start_bit=start)
+                        assert y.cpu().numpy().tobytes() == ref_out.tobytes()
+
+
+def test_header_roundtrip_device_stream(zb, port):
+    """zfp_write_header on a device-resident stream followed by compress: the payload starts at
+    bit 96 and the header survives (the reference CUDA path overwrites it, execution.rst:203-204)."""
+    import torch
+    a = analytic_field((33, 40, 36), np.float64)
+    x = torch.from_numpy(a).cuda()
+    for mode in ({"rate": 8}, {"accuracy": 1e-4}):
+        c = zb.compress(x, header=True, **mode)
+        words = c.to_numpy()
+        payload, end = port.compress_raw(a.reshape(-1), 0, a.dtype, [36, 40, 33, 0], None, mode, start_bit=96,
+                                         prefix_words=words[:2] & np.array([2 ** 64 - 1, 2 ** 32 - 1], dtype=np.uint64))
+        assert words.tobytes() == payload.tobytes()
+        assert bytes(words[:1].tobytes()[:4]) == b"zfp\x05"
+        back = zb.decompress(c, header=True)
+        want = np.zeros_like(a)
+        port.decompress_raw(payload, want.reshape(-1), 0, a.dtype, [36, 40, 33, 0], None, mode, start_bit=96)
+        assert back.cpu().numpy().tobytes() == want.tobytes()

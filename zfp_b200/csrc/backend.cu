@@ -1,0 +1,585 @@
+// backend.cu - the thin C-ABI layer between zfp's host dispatch and the sm_100a kernels.
+//
+// Replaces the reference's src/cuda_zfp/cuZFP.cu (entry points cuda_compress :357-414 and
+// cuda_decompress :416-491) with the same signatures and the same post-conditions on the host
+// bitstream, but supports every compression mode, a non-zero stream offset, strided and
+// partial-block fields, 64-bit block counts, and keeps everything on the caller's device.
+//
+// There is no CPU code path in this file: if a CUDA call fails the entry points return failure.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/zfp_b200_backend.h"
+#include "bitstream_impl.h"
+#include "kernels.cuh"
+#include "kernels4d.cuh"
+
+using namespace zb;
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static bool cuda_ok(cudaError_t e, const char* what)
+{
+  if (e == cudaSuccess) return true;
+  g_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+#define CU(call) do { if (!cuda_ok((call), #call)) return ZFP_B200_ECUDA; } while (0)
+#define LAUNCHED() do { g_launches.fetch_add(1, std::memory_order_relaxed); \
+                        if (!cuda_ok(cudaGetLastError(), "kernel launch")) return ZFP_B200_ECUDA; } while (0)
+
+extern "C" const char* zfp_b200_last_error(void) { return g_error.c_str(); }
+extern "C" uint64 zfp_b200_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// device scratch: grow-only buffers cached per (device, slot), released on request
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+enum { SCR_SLOTS = 0, SCR_LENGTHS, SCR_TILES, SCR_OFFSETS, SCR_CURSOR, SCR_STAGE_DATA, SCR_STAGE_WORDS, SCR_COUNT };
+
+struct ScratchBuf { void* p = nullptr; size_t bytes = 0; };
+struct DeviceScratch { ScratchBuf buf[SCR_COUNT]; };
+std::mutex g_scratch_mutex;
+DeviceScratch g_scratch[64];
+
+void* scratch(int slot, size_t bytes)
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  ScratchBuf& b = g_scratch[dev].buf[slot];
+  if (b.bytes < bytes) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    if (!cuda_ok(cudaMalloc(&b.p, want), "cudaMalloc(scratch)")) return nullptr;
+    b.bytes = want;
+  }
+  return b.p;
+}
+
+}  // namespace
+
+extern "C" void zfp_b200_release_scratch(void)
+{
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 64; d++)
+    for (int s = 0; s < SCR_COUNT; s++)
+      if (g_scratch[d].buf[s].p) {
+        cudaSetDevice(d);
+        cudaFree(g_scratch[d].buf[s].p);
+        g_scratch[d].buf[s] = ScratchBuf();
+      }
+  cudaSetDevice(cur);
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-offset index
+// ------------------------------------------------------------------------------------------------
+struct zfp_b200_index {
+  uint16_t* d_lengths = nullptr;
+  size_t blocks = 0;
+  size_t capacity = 0;
+};
+
+extern "C" zfp_b200_index* zfp_b200_index_create(void) { return new (std::nothrow) zfp_b200_index(); }
+
+extern "C" void zfp_b200_index_destroy(zfp_b200_index* ix)
+{
+  if (!ix) return;
+  if (ix->d_lengths) cudaFree(ix->d_lengths);
+  delete ix;
+}
+
+static bool index_reserve(zfp_b200_index* ix, size_t blocks)
+{
+  if (ix->capacity < blocks) {
+    if (ix->d_lengths) cudaFree(ix->d_lengths);
+    ix->d_lengths = nullptr;
+    ix->capacity = 0;
+    if (!cuda_ok(cudaMalloc(&ix->d_lengths, blocks * sizeof(uint16_t) + 64), "cudaMalloc(index)")) return false;
+    ix->capacity = blocks;
+  }
+  ix->blocks = blocks;
+  return true;
+}
+
+extern "C" size_t zfp_b200_index_blocks(const zfp_b200_index* ix) { return ix ? ix->blocks : 0; }
+
+extern "C" size_t zfp_b200_index_export(const zfp_b200_index* ix, uint16_t* host, size_t capacity)
+{
+  if (!ix || !host || capacity < ix->blocks) return 0;
+  if (!cuda_ok(cudaMemcpy(host, ix->d_lengths, ix->blocks * sizeof(uint16_t), cudaMemcpyDeviceToHost), "index export"))
+    return 0;
+  return ix->blocks;
+}
+
+extern "C" int zfp_b200_index_import(zfp_b200_index* ix, const uint16_t* host, size_t blocks)
+{
+  if (!ix || !host) return ZFP_B200_EINVAL;
+  if (!index_reserve(ix, blocks)) return ZFP_B200_ECUDA;
+  CU(cudaMemcpy(ix->d_lengths, host, blocks * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  return ZFP_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry and parameters
+// ------------------------------------------------------------------------------------------------
+static size_t scalar_bytes(int type) { return (type == T_INT32 || type == T_FLOAT) ? 4 : 8; }
+
+static bool make_geom(const zfp_b200_desc* d, const void* data, Geom* g)
+{
+  if (!d || d->dims < 1 || d->dims > 4 || d->type < T_INT32 || d->type > T_DOUBLE) return false;
+  int64_t contiguous = 1;
+  g->nblocks = 1;
+  for (uint32_t i = 0; i < 4; i++) {
+    uint64_t n = i < d->dims ? d->n[i] : 1;
+    if (i < d->dims && n == 0) return false;
+    g->n[i] = n;
+    g->s[i] = (i < d->dims && d->s[i]) ? (int64_t)d->s[i] : contiguous;
+    g->nb[i] = (n + 3) / 4;
+    g->nblocks *= g->nb[i];
+    contiguous *= (int64_t)n;
+  }
+  const size_t row = 4 * scalar_bytes(d->type);
+  bool vec = g->s[0] == 1 && (reinterpret_cast<uintptr_t>(data) % row) == 0;
+  for (uint32_t i = 1; i < d->dims; i++)
+    vec = vec && (g->s[i] % 4) == 0;
+  g->vec_rows = vec ? 1 : 0;
+  return true;
+}
+
+static bool check_params(const zfp_b200_desc* d)
+{
+  return d->minbits <= d->maxbits && d->maxprec >= 1 && d->maxprec <= 64 && d->maxbits >= 1;
+}
+
+// worst-case coded size of one block (the per-block term of zfp_stream_maximum_size, src/zfp.c:711-742)
+static uint32_t block_capacity_bits(const zfp_b200_desc* d)
+{
+  const bool reversible = d->minexp < kMinExp;
+  const uint32_t values = 1u << (2 * d->dims), prec = (uint32_t)(8 * scalar_bytes(d->type));
+  uint32_t bits = 0;
+  switch (d->type) {
+    case T_INT32: bits = reversible ? 5 : 0; break;
+    case T_INT64: bits = reversible ? 6 : 0; break;
+    case T_FLOAT: bits = reversible ? 15 : 9; break;
+    default: bits = reversible ? 19 : 12; break;
+  }
+  bits += values - 1 + values * (d->maxprec < prec ? d->maxprec : prec);
+  if (bits > d->maxbits) bits = d->maxbits;
+  if (bits < d->minbits) bits = d->minbits;
+  return bits;
+}
+
+extern "C" int zfp_b200_is_fixed_rate(const zfp_b200_desc* d) { return d && d->minbits == d->maxbits; }
+
+extern "C" size_t zfp_b200_blocks(const zfp_b200_desc* d)
+{
+  Geom g;
+  return make_geom(d, nullptr, &g) ? (size_t)g.nblocks : 0;
+}
+
+extern "C" size_t zfp_b200_capacity(const zfp_b200_desc* d, uint64 start_bit)
+{
+  Geom g;
+  if (!make_geom(d, nullptr, &g)) return 0;
+  uint64_t bits = start_bit + 148 + g.nblocks * (uint64_t)block_capacity_bits(d);
+  return (size_t)(((bits + 63) & ~(uint64_t)63) / 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+template <int TYPE, int DIMS>
+static size_t plane_smem_bytes()
+{
+  constexpr int N = 1 << (2 * DIMS);
+  return (size_t)(kThreads / 32) * Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type);
+}
+
+template <class K>
+static bool allow_smem(K kernel, size_t bytes)
+{
+  return bytes <= 48 * 1024 ||
+         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute");
+}
+
+template <int TYPE, int DIMS, int OUT>
+static int launch_encode(const void* data, const Geom& g, const Params& prm, void* out, uint64_t start_bit,
+                         uint32_t slot_words, uint16_t* lengths, uint64_t b0, uint64_t b1, cudaStream_t st)
+{
+  auto kernel = encode_kernel<TYPE, DIMS, OUT>;
+  const size_t smem = plane_smem_bytes<TYPE, DIMS>();
+  if (!allow_smem(kernel, smem)) return ZFP_B200_ECUDA;
+  const uint64_t ctas = (b1 - b0 + kThreads - 1) / kThreads;
+  kernel<<<(unsigned)ctas, kThreads, smem, st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(data), g, prm, out,
+                                                  start_bit, slot_words, lengths, b0, b1);
+  LAUNCHED();
+  return ZFP_B200_OK;
+}
+
+template <int TYPE, int DIMS, int OFFS>
+static int launch_decode(void* data, const Geom& g, const Params& prm, const void* in, uint64_t start_bit,
+                         const uint64_t* offsets, cudaStream_t st)
+{
+  auto kernel = decode_kernel<TYPE, DIMS, OFFS>;
+  const size_t smem = plane_smem_bytes<TYPE, DIMS>();
+  if (!allow_smem(kernel, smem)) return ZFP_B200_ECUDA;
+  const uint64_t ctas = (g.nblocks + kThreads - 1) / kThreads;
+  kernel<<<(unsigned)ctas, kThreads, smem, st>>>(static_cast<typename Traits<TYPE>::Scalar*>(data), g, prm, in, start_bit, offsets);
+  LAUNCHED();
+  return ZFP_B200_OK;
+}
+
+// runtime (type, dims) -> template instance
+#define ZB_DISPATCH(FN, ...)                                                              \
+  switch (type * 10 + (int)dims) {                                                        \
+    case 11: return FN<T_INT32, 1, MODE>(__VA_ARGS__);                                    \
+    case 12: return FN<T_INT32, 2, MODE>(__VA_ARGS__);                                    \
+    case 13: return FN<T_INT32, 3, MODE>(__VA_ARGS__);                                    \
+    case 21: return FN<T_INT64, 1, MODE>(__VA_ARGS__);                                    \
+    case 22: return FN<T_INT64, 2, MODE>(__VA_ARGS__);                                    \
+    case 23: return FN<T_INT64, 3, MODE>(__VA_ARGS__);                                    \
+    case 31: return FN<T_FLOAT, 1, MODE>(__VA_ARGS__);                                    \
+    case 32: return FN<T_FLOAT, 2, MODE>(__VA_ARGS__);                                    \
+    case 33: return FN<T_FLOAT, 3, MODE>(__VA_ARGS__);                                    \
+    case 41: return FN<T_DOUBLE, 1, MODE>(__VA_ARGS__);                                   \
+    case 42: return FN<T_DOUBLE, 2, MODE>(__VA_ARGS__);                                   \
+    case 43: return FN<T_DOUBLE, 3, MODE>(__VA_ARGS__);                                   \
+    default: return ZFP_B200_EINVAL;                                                      \
+  }
+
+template <int MODE>
+static int encode_any(int type, uint32_t dims, const void* data, const Geom& g, const Params& prm, void* out,
+                      uint64_t start_bit, uint32_t slot_words, uint16_t* lengths, uint64_t b0, uint64_t b1, cudaStream_t st)
+{
+  if (dims == 4) return launch_encode4<MODE>(type, data, g, prm, out, start_bit, slot_words, lengths, b0, b1, st, g_launches);
+  ZB_DISPATCH(launch_encode, data, g, prm, out, start_bit, slot_words, lengths, b0, b1, st)
+}
+
+template <int MODE>
+static int decode_any(int type, uint32_t dims, void* data, const Geom& g, const Params& prm, const void* in,
+                      uint64_t start_bit, const uint64_t* offsets, cudaStream_t st)
+{
+  if (dims == 4) return launch_decode4<MODE>(type, data, g, prm, in, start_bit, offsets, st, g_launches);
+  ZB_DISPATCH(launch_decode, data, g, prm, in, start_bit, offsets, st)
+}
+
+// exclusive scan of `n` block lengths into bit offsets, continuing at cursor[1]
+static int scan_lengths(const uint16_t* lengths, uint64_t n, uint64_t* tiles, uint64_t* offsets, uint64_t* cursor,
+                        cudaStream_t st)
+{
+  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  scan_tile_sums<<<(unsigned)ntiles, kScanThreads, 0, st>>>(lengths, n, tiles);
+  LAUNCHED();
+  scan_tile_offsets<<<1, 1024, 0, st>>>(tiles, ntiles, cursor);
+  LAUNCHED();
+  scan_apply<<<(unsigned)ntiles, kScanThreads, 0, st>>>(lengths, n, tiles, offsets);
+  LAUNCHED();
+  return ZFP_B200_OK;
+}
+
+__global__ void set_cursor(uint64_t* cursor, uint64_t v) { cursor[0] = v; cursor[1] = v; }
+
+// ------------------------------------------------------------------------------------------------
+// raw entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void* d_words, uint64 start_bit,
+                               uint64* end_bit, zfp_b200_index* index, void* cuda_stream)
+{
+  Geom g;
+  if (!make_geom(d, d_data, &g) || !check_params(d) || !d_data || !d_words) {
+    g_error = "zfp_b200_encode: invalid descriptor";
+    return ZFP_B200_EINVAL;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
+  const int type = d->type;
+  const uint32_t dims = d->dims;
+  int rc;
+
+  if (d->minbits == d->maxbits) {
+    // fixed rate: block b lives at start + b*maxbits, no communication between blocks
+    const uint64_t total = g.nblocks * (uint64_t)d->maxbits, end = start_bit + total;
+    if ((start_bit & 63) == 0 && (d->maxbits & 63) == 0)
+      rc = encode_any<0>(type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
+    else {
+      uint64_t* w = static_cast<uint64_t*>(d_words);
+      const uint64_t w0 = (start_bit + 63) >> 6, w1 = (end + 63) >> 6;
+      clear_word_tail<<<1, 1, 0, st>>>(w, start_bit);
+      LAUNCHED();
+      if (w1 > w0) CU(cudaMemsetAsync(w + w0, 0, (w1 - w0) * 8, st));
+      rc = encode_any<1>(type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
+    }
+    if (rc) return rc;
+    if (end_bit) *end_bit = end;
+    return ZFP_B200_OK;
+  }
+
+  // variable rate: encode into per-block scratch slots, scan the lengths, compact bit-granularly
+  const uint32_t slot_words = (block_capacity_bits(d) + 63) / 64;
+  const uint64_t slot_bytes = (uint64_t)slot_words * 8;
+  uint64_t chunk = ((uint64_t)1 << 30) / slot_bytes;
+  chunk = chunk / kScanTile * kScanTile;
+  if (chunk < (uint64_t)kScanTile) chunk = kScanTile;
+  if (chunk > g.nblocks) chunk = g.nblocks;
+
+  uint16_t* lengths;
+  if (index) {
+    if (!index_reserve(index, g.nblocks)) return ZFP_B200_ECUDA;
+    lengths = index->d_lengths;
+  }
+  else
+    lengths = static_cast<uint16_t*>(scratch(SCR_LENGTHS, g.nblocks * sizeof(uint16_t)));
+  uint64_t* slots = static_cast<uint64_t*>(scratch(SCR_SLOTS, chunk * slot_bytes));
+  uint64_t* tiles = static_cast<uint64_t*>(scratch(SCR_TILES, ((chunk + kScanTile - 1) / kScanTile + 1) * 8));
+  uint64_t* offsets = static_cast<uint64_t*>(scratch(SCR_OFFSETS, chunk * 8));
+  uint64_t* cursor = static_cast<uint64_t*>(scratch(SCR_CURSOR, 64));
+  if (!lengths || !slots || !tiles || !offsets || !cursor) return ZFP_B200_ECUDA;
+
+  set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
+  LAUNCHED();
+  clear_word_tail<<<1, 1, 0, st>>>(static_cast<uint64_t*>(d_words), start_bit);
+  LAUNCHED();
+  for (uint64_t b0 = 0; b0 < g.nblocks; b0 += chunk) {
+    const uint64_t b1 = b0 + chunk < g.nblocks ? b0 + chunk : g.nblocks, cn = b1 - b0;
+    rc = encode_any<2>(type, dims, d_data, g, prm, slots, 0, slot_words, lengths, b0, b1, st);
+    if (rc) return rc;
+    rc = scan_lengths(lengths + b0, cn, tiles, offsets, cursor, st);
+    if (rc) return rc;
+    zero_new_words<<<148 * 4, 256, 0, st>>>(static_cast<uint64_t*>(d_words), cursor);
+    LAUNCHED();
+    compact_blocks<<<(unsigned)((cn + 255) / 256), 256, 0, st>>>(slots, slot_words, lengths + b0, offsets, cn, d_words);
+    LAUNCHED();
+  }
+  uint64_t h_cursor[2];
+  CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (end_bit) *end_bit = h_cursor[1];
+  return ZFP_B200_OK;
+}
+
+extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
+                               uint64* end_bit, const zfp_b200_index* index, void* cuda_stream)
+{
+  Geom g;
+  if (!make_geom(d, d_data, &g) || !check_params(d) || !d_data || !d_words) {
+    g_error = "zfp_b200_decode: invalid descriptor";
+    return ZFP_B200_EINVAL;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
+  int rc;
+
+  if (d->minbits == d->maxbits) {
+    rc = decode_any<0>(d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, st);
+    if (rc) return rc;
+    if (end_bit) *end_bit = start_bit + g.nblocks * (uint64_t)d->maxbits;
+    return ZFP_B200_OK;
+  }
+
+  if (!index || index->blocks != g.nblocks) {
+    g_error = "zfp_b200_decode: variable-rate stream needs a block index with one entry per block";
+    return ZFP_B200_ENOINDEX;
+  }
+  uint64_t* tiles = static_cast<uint64_t*>(scratch(SCR_TILES, ((g.nblocks + kScanTile - 1) / kScanTile + 1) * 8));
+  uint64_t* offsets = static_cast<uint64_t*>(scratch(SCR_OFFSETS, g.nblocks * 8));
+  uint64_t* cursor = static_cast<uint64_t*>(scratch(SCR_CURSOR, 64));
+  if (!tiles || !offsets || !cursor) return ZFP_B200_ECUDA;
+  set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
+  LAUNCHED();
+  rc = scan_lengths(index->d_lengths, g.nblocks, tiles, offsets, cursor, st);
+  if (rc) return rc;
+  rc = decode_any<1>(d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, st);
+  if (rc) return rc;
+  uint64_t h_cursor[2];
+  CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (end_bit) *end_bit = h_cursor[1];
+  return ZFP_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// zfp_stream / zfp_field entry points (drop-in for src/cuda_zfp/cuZFP.h:9-10)
+// ------------------------------------------------------------------------------------------------
+static bool on_device(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static bool fill_desc(const zfp_stream* zfp, const zfp_field* f, zfp_b200_desc* d)
+{
+  memset(d, 0, sizeof(*d));
+  d->type = (int)f->type;
+  d->dims = f->nx ? f->ny ? f->nz ? f->nw ? 4 : 3 : 2 : 1 : 0;
+  if (!d->dims) return false;
+  d->n[0] = f->nx; d->n[1] = f->ny; d->n[2] = f->nz; d->n[3] = f->nw;
+  d->s[0] = f->sx; d->s[1] = f->sy; d->s[2] = f->sz; d->s[3] = f->sw;
+  d->minbits = zfp->minbits; d->maxbits = zfp->maxbits; d->maxprec = zfp->maxprec; d->minexp = zfp->minexp;
+  return true;
+}
+
+// lowest and highest element index touched by the field (src/zfp.c field_index_span)
+static void index_span(const zfp_b200_desc* d, int64_t* lo, int64_t* hi)
+{
+  Geom g;
+  make_geom(d, nullptr, &g);
+  *lo = *hi = 0;
+  for (uint32_t i = 0; i < d->dims; i++) {
+    int64_t reach = g.s[i] * (int64_t)(g.n[i] - 1);
+    if (reach < 0) *lo += reach; else *hi += reach;
+  }
+}
+
+static zfp_exec_params_cuda* get_cuda_params(const zfp_stream* zfp)
+{
+  if (zfp->exec.policy != zfp_exec_cuda || !zfp->exec.params) return nullptr;
+  zfp_exec_params_cuda* p = static_cast<zfp_exec_params_cuda*>(zfp->exec.params);
+  return p->magic == ZFP_B200_PARAMS_MAGIC ? p : nullptr;
+}
+
+static size_t compress_impl(zfp_stream* zfp, const zfp_field* field)
+{
+  zfp_b200_desc d;
+  bitstream* s = zfp->stream;
+  if (!s || !field->data || !fill_desc(zfp, field, &d)) return 0;
+  zfp_exec_params_cuda* xp = get_cuda_params(zfp);
+  cudaStream_t st = xp ? static_cast<cudaStream_t>(xp->cuda_stream) : nullptr;
+  const size_t esize = scalar_bytes(d.type);
+  const uint64_t start_bit = (uint64_t)(s->ptr - s->begin) * 64 + s->bits;
+  const uint64_t first_word = start_bit >> 6;
+
+  // field data: use in place when device resident, else stage the touched span
+  int64_t lo, hi;
+  index_span(&d, &lo, &hi);
+  const void* d_data = field->data;
+  if (!on_device(field->data)) {
+    const size_t bytes = (size_t)(hi - lo + 1) * esize;
+    char* stage = static_cast<char*>(scratch(SCR_STAGE_DATA, bytes));
+    if (!stage) return 0;
+    if (!cuda_ok(cudaMemcpyAsync(stage, static_cast<const char*>(field->data) + lo * (int64_t)esize, bytes,
+                                 cudaMemcpyHostToDevice, st), "H2D field")) return 0;
+    d_data = stage - lo * (int64_t)esize;
+  }
+
+  // stream buffer: same
+  const bool stream_dev = on_device(s->begin);
+  const size_t cap_bytes = zfp_b200_capacity(&d, start_bit & 63) + 8;
+  uint64_t* d_words;
+  if (stream_dev)
+    d_words = s->begin + first_word;
+  else {
+    d_words = static_cast<uint64_t*>(scratch(SCR_STAGE_WORDS, cap_bytes));
+    if (!d_words) return 0;
+  }
+  // bits of a partially filled word (e.g. a header) still sit in the host-side buffer
+  if (s->bits) {
+    const uint64_t partial = s->buffer & ((1ull << s->bits) - 1);
+    if (!cuda_ok(cudaMemcpyAsync(d_words, &partial, 8, cudaMemcpyHostToDevice, st), "H2D partial word")) return 0;
+    if (!cuda_ok(cudaStreamSynchronize(st), "sync")) return 0;
+  }
+
+  zfp_b200_index* index = nullptr;
+  if (d.minbits != d.maxbits && xp) {
+    if (!xp->index) xp->index = zfp_b200_index_create();
+    index = xp->index;
+  }
+  uint64_t end_rel = 0;
+  if (zfp_b200_encode(&d, d_data, d_words, start_bit & 63, &end_rel, index, st) != ZFP_B200_OK) return 0;
+  const uint64_t words_rel = (end_rel + 63) >> 6;
+
+  if (!stream_dev) {
+    if (!cuda_ok(cudaMemcpyAsync(s->begin + first_word, d_words, words_rel * 8, cudaMemcpyDeviceToHost, st), "D2H stream"))
+      return 0;
+  }
+  if (!(xp && xp->device_only_sync && stream_dev && d.minbits == d.maxbits))
+    if (!cuda_ok(cudaStreamSynchronize(st), "sync")) return 0;
+
+  // leave the host bitstream flushed and positioned after the last word (cuZFP.cu:406-411)
+  s->ptr = s->begin + first_word + words_rel;
+  s->bits = 0;
+  s->buffer = 0;
+  return (size_t)(s->ptr - s->begin) * 8;
+}
+
+static size_t decompress_impl(zfp_stream* zfp, zfp_field* field)
+{
+  zfp_b200_desc d;
+  bitstream* s = zfp->stream;
+  if (!s || !field->data || !fill_desc(zfp, field, &d)) return 0;
+  zfp_exec_params_cuda* xp = get_cuda_params(zfp);
+  cudaStream_t st = xp ? static_cast<cudaStream_t>(xp->cuda_stream) : nullptr;
+  const size_t esize = scalar_bytes(d.type);
+  const uint64_t start_bit = (uint64_t)(s->ptr - s->begin) * 64 - s->bits;
+  const uint64_t first_word = start_bit >> 6;
+
+  int64_t lo, hi;
+  index_span(&d, &lo, &hi);
+  const bool data_dev = on_device(field->data);
+  const size_t span_bytes = (size_t)(hi - lo + 1) * esize;
+  void* d_data = field->data;
+  char* stage = nullptr;
+  if (!data_dev) {
+    stage = static_cast<char*>(scratch(SCR_STAGE_DATA, span_bytes));
+    if (!stage) return 0;
+    // gaps of a strided host array must survive the round trip
+    if ((uint64_t)(hi - lo + 1) != (uint64_t)(d.n[0] * (d.dims > 1 ? d.n[1] : 1) * (d.dims > 2 ? d.n[2] : 1) * (d.dims > 3 ? d.n[3] : 1)))
+      if (!cuda_ok(cudaMemcpyAsync(stage, static_cast<char*>(field->data) + lo * (int64_t)esize, span_bytes,
+                                   cudaMemcpyHostToDevice, st), "H2D field")) return 0;
+    d_data = stage - lo * (int64_t)esize;
+  }
+
+  const bool stream_dev = on_device(s->begin);
+  const uint64_t* d_words;
+  if (stream_dev)
+    d_words = s->begin + first_word;
+  else {
+    size_t want = zfp_b200_capacity(&d, start_bit & 63);
+    const size_t have = (size_t)(s->end - (s->begin + first_word)) * 8;
+    if (s->end > s->begin && want > have) want = have;
+    uint64_t* w = static_cast<uint64_t*>(scratch(SCR_STAGE_WORDS, want + 16));
+    if (!w) return 0;
+    if (!cuda_ok(cudaMemcpyAsync(w, s->begin + first_word, want, cudaMemcpyHostToDevice, st), "H2D stream")) return 0;
+    d_words = w;
+  }
+
+  const zfp_b200_index* index = (d.minbits != d.maxbits && xp) ? xp->index : nullptr;
+  uint64_t end_rel = 0;
+  if (zfp_b200_decode(&d, d_data, d_words, start_bit & 63, &end_rel, index, st) != ZFP_B200_OK) return 0;
+
+  if (!data_dev)
+    if (!cuda_ok(cudaMemcpyAsync(static_cast<char*>(field->data) + lo * (int64_t)esize, stage, span_bytes,
+                                 cudaMemcpyDeviceToHost, st), "D2H field")) return 0;
+  if (!(xp && xp->device_only_sync && data_dev && d.minbits == d.maxbits))
+    if (!cuda_ok(cudaStreamSynchronize(st), "sync")) return 0;
+
+  s->ptr = s->begin + first_word + ((end_rel + 63) >> 6);
+  s->bits = 0;
+  s->buffer = 0;
+  return (size_t)(s->ptr - s->begin) * 8;
+}
+
+extern "C" size_t zfp_b200_compress_stream(zfp_stream* stream, const zfp_field* field) { return compress_impl(stream, field); }
+extern "C" size_t zfp_b200_decompress_stream(zfp_stream* stream, zfp_field* field) { return decompress_impl(stream, field); }
+extern "C" size_t cuda_compress(zfp_stream* stream, const zfp_field* field) { return compress_impl(stream, field); }
+extern "C" void cuda_decompress(zfp_stream* stream, zfp_field* field) { decompress_impl(stream, field); }
