@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark of the zfp hot path on B200 (see BASELINE.json / DESIGN.md).
+
+One "step" = zfp_compress followed by zfp_decompress of one device-resident slab of a synthetic
+smooth 3-D fp64 field at fixed rate 8 bits/value (BASELINE.json configs[1]: 1024^3 fp64, rate 8).
+With N GPUs the global field is (1024*N) x 1024 x 1024 split into N block-aligned slabs along the
+slowest dimension, one per rank, no data-path collective (fixed-rate slabs sit at deterministic bit
+offsets) -> weak scaling.
+
+metric = (uncompressed bytes compressed + uncompressed bytes decompressed) / time, GB = 1e9 B.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "compress+decompress GB/s (uncompressed), 3D fp64 fixed-rate"
+UNIT = "GB/s"
+RATE = 8
+SIDE = 1024          # per-GPU slab is SIDE^3 values (8 GiB fp64)
+CPU_SIDE = 512       # bounded CPU sample: CPU_SIDE^3 sub-box of the same field (1 GiB)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def field_slab(torch, rank, nz, ny, nx, device):
+    """SURVEY 8(d) S1 analytic smooth field, slab `rank` of the global array, generated on device."""
+    gz = torch.arange(rank * nz, (rank + 1) * nz, device=device, dtype=torch.float64) / (nz * max(1, int(os.environ.get("WORLD_SIZE", "1"))) - 1)
+    gy = torch.arange(ny, device=device, dtype=torch.float64) / (ny - 1)
+    gx = torch.arange(nx, device=device, dtype=torch.float64) / (nx - 1)
+    out = torch.empty((nz, ny, nx), dtype=torch.float64, device=device)
+    chunk = 64
+    for z0 in range(0, nz, chunk):
+        z = gz[z0:z0 + chunk, None, None]
+        y = gy[None, :, None]
+        x = gx[None, None, :]
+        out[z0:z0 + chunk] = torch.sin(2 * np.pi * (3 * x + 0.5 * y)) * torch.cos(4 * np.pi * z) + 0.25 * torch.sin(14 * np.pi * x * y * z)
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([v.strip() for v in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref), all host threads it can use
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample_field(side):
+    ax = np.linspace(0.0, 1.0, SIDE)[:side]
+    z, y, x = ax[:, None, None], ax[None, :, None], ax[None, None, :]
+    return np.ascontiguousarray(np.sin(2 * np.pi * (3 * x + 0.5 * y)) * np.cos(4 * np.pi * z) + 0.25 * np.sin(14 * np.pi * x * y * z))
+
+
+def time_reference(a, steps, warmup, threads):
+    """compress with zfp_exec_omp (all threads) + decompress serial (the reference has no parallel
+    decompress, src/zfp.c:1137-1138); returns per-step seconds (compress, decompress), stream words."""
+    from oracle.oracle import Reference
+    R = Reference()
+    n = list(reversed(a.shape)) + [0]
+    flat = a.reshape(-1)
+    out = np.empty_like(a)
+    buf = np.zeros(R.maximum_size({"rate": RATE}, a.dtype, n) // 8 + 4, dtype=np.uint64)
+    tc, td, words = [], [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        words, _ = R.compress_raw(flat, 0, a.dtype, n, None, {"rate": RATE}, policy=R.OMP if threads > 1 else R.SERIAL,
+                                  threads=threads, out=buf)
+        t1 = time.perf_counter()
+        R.decompress_raw_noalloc(words, out.reshape(-1), a.dtype, n, {"rate": RATE})
+        t2 = time.perf_counter()
+        if i >= warmup:
+            tc.append(t1 - t0)
+            td.append(t2 - t1)
+    return tc, td, words, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    a = cpu_sample_field(CPU_SIDE)
+    tc, td, _, _ = time_reference(a, args.steps, args.warmup, threads)
+    step = float(np.sum(tc) + np.sum(td)) / args.steps
+    value = 2 * a.nbytes / step / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D fp64 %d^3 per GPU, fixed-rate %d, compress+decompress" % (SIDE, RATE),
+                   "sample": "%d^3 sub-box of the same analytic field per step" % CPU_SIDE},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": "%d^3 fp64 sub-box (%.2f GiB) per step; zfp_exec_omp compress with %d threads (%.3f GB/s) + serial decompress (%.3f GB/s; reference has no parallel decompress)"
+                                   % (CPU_SIDE, a.nbytes / 2 ** 30, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import zfp_b200 as zb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    zb.load_library(build_if_missing=False)
+
+    nz = ny = nx = SIDE
+    x = field_slab(torch, rank, nz, ny, nx, dev)
+    raw_bytes = x.numel() * 8
+    mode = {"rate": RATE}
+    words = torch.empty(zb.max_stream_words(x.shape, x.dtype, mode), dtype=torch.int64, device=dev)
+    y = torch.empty_like(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(record=None):
+        if record: record[0].record()
+        c = zb.compress(x, out=words, async_fixed_rate=True, **mode)
+        if record: record[1].record()
+        zb.decompress(c, out=y)
+        if record: record[2].record()
+        return c
+
+    for _ in range(max(args.warmup, 3)):
+        c = step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = zb.launch_count()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record()
+    for i in range(args.steps):
+        c = step(evs[i])
+    t_end.record()
+    barrier()
+    launches = zb.launch_count() - launches0
+    clocks = sampler.finish()
+    total_ms = t_begin.elapsed_time(t_end)
+    enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    tmax = torch.tensor([total_ms, enc_ms, dec_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms, enc_ms, dec_ms = [float(v) for v in tmax.tolist()]
+    ms_per_step = total_ms / args.steps
+    value = 2 * raw_bytes * world / (ms_per_step * 1e-3) / 1e9
+    comp_bytes = c.nbytes
+
+    # ---- end to end through the public C API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    try:
+        hx = torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True)
+        hx.copy_(x)
+        hy = torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True)
+        hw = torch.zeros(words.numel(), dtype=torch.int64, pin_memory=True)
+        L = zb.load_library()
+        from zfp_b200.api import Stream, _make_field
+        s = Stream(hw.data_ptr(), hw.numel() * 8, mode, 4, 3)
+        fin = _make_field(L, hx.data_ptr(), 4, (nz, ny, nx), None)
+        fout = _make_field(L, hy.data_ptr(), 4, (nz, ny, nx), None)
+
+        def e2e_step():
+            L.zfp_stream_rewind(s.z)
+            nb = L.zfp_compress(s.z, fin)       # H2D field, kernels, D2H stream
+            L.zfp_stream_rewind(s.z)
+            nb2 = L.zfp_decompress(s.z, fout)   # H2D stream, kernels, D2H field
+            assert nb == nb2 == comp_bytes, (nb, nb2, comp_bytes)
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": 2 * raw_bytes * world / (float(dt.item()) / e2e_steps) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": raw_bytes + comp_bytes, "d2h_bytes_per_step": raw_bytes + comp_bytes,
+               "steps": e2e_steps, "note": "zfp_compress/zfp_decompress on pinned host field + host stream buffer"}
+        same = bool(torch.equal(hy, y.cpu()))
+        e2e["matches_device_path"] = same
+        L.zfp_field_free(fin)
+        L.zfp_field_free(fout)
+        s.close()
+        del hx, hy, hw
+    except Exception as ex:  # report, never fake
+        e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    values = x.numel()
+    enc_alg = values * (8 + RATE / 8.0)   # bytes: read fp64 + write RATE bits per value
+    dec_alg = enc_alg
+    roof_enc = {"kernel": "encode_kernel<double,3,aligned>", "bound": "hbm", "achieved": enc_alg / (enc_ms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src, "ms": enc_ms}
+    roof_enc["frac"] = roof_enc["achieved"] / peak
+    roof_dec = {"kernel": "decode_kernel<double,3,fixed>", "bound": "hbm", "achieved": dec_alg / (dec_ms * 1e-3) / 1e9,
+                "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src, "ms": dec_ms}
+    roof_dec["frac"] = roof_dec["achieved"] / peak
+    dominant = roof_dec if dec_ms >= enc_ms else roof_enc
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "3D fp64 %dx%dx%d per GPU (global %dx%dx%d), fixed-rate %d bits/value, zfp_compress + zfp_decompress, device resident"
+                               % (nz, ny, nx, nz * world, ny, nx, RATE),
+                   "parallelism": "slab-per-GPU x%d, no collective" % world,
+                   "l2": "inputs (8 GiB) and outputs exceed the 126 MB L2; no explicit flush"},
+        "compress_gbs": raw_bytes * world / (enc_ms * 1e-3) / 1e9, "decompress_gbs": raw_bytes * world / (dec_ms * 1e-3) / 1e9,
+        "compressed_bytes_per_gpu": comp_bytes,
+        "roofline": dominant, "roofline_encode": roof_enc, "roofline_decode": roof_dec,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+    }
+
+    # ---- CPU baseline on this box's host cores (N=1 only), bounded sample, plus a parity check on it
+    if world == 1 and not args.no_cpu:
+        try:
+            threads = os.cpu_count() or 1
+            side = CPU_SIDE if not args.quick else 256
+            a = x[:side, :side, :side].contiguous().cpu().numpy()
+            tc, td, ref_words, ref_out = time_reference(a, 2, 1, threads)
+            tcs, tds, _, _ = time_reference(a[: side // 2], 1, 0, 1)
+            cs = zb.compress(torch.from_numpy(a).to(dev), **mode)
+            parity = cs.to_numpy().tobytes() == ref_words.tobytes() and zb.decompress(cs).cpu().numpy().tobytes() == ref_out.tobytes()
+            val = 2 * a.nbytes / (np.mean(tc) + np.mean(td)) / 1e9
+            line["cpu_baseline"] = {
+                "value": val, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": "%d^3 sub-box of the bench field; zfp_exec_omp compress x%d threads %.3f GB/s + serial decompress %.3f GB/s (no parallel decompress upstream); serial compress %.3f GB/s on half the sample"
+                          % (side, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9, a.nbytes / 2 / np.mean(tcs) / 1e9),
+                "stream_and_array_bit_identical_to_gpu": bool(parity)}
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "error": repr(ex)[:200]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="smaller CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

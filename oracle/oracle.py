@@ -302,6 +302,20 @@ class Reference:
         L.stream_close(bs)
         return nbytes
 
+    def decompress_raw_noalloc(self, words, buf, dtype, n, mode):
+        """decompress_raw without the defensive copy of the stream (for timing); `words` must be
+        followed by at least one readable word (true for views of a capacity-sized buffer)."""
+        L = self.L
+        f, dims = self._field(buf.ctypes.data, dtype, n, None)
+        bs = L.stream_open(words.ctypes.data, words.nbytes)
+        z = L.zfp_stream_open(bs)
+        self._set_mode(z, mode, dtype, dims)
+        nbytes = L.zfp_decompress(z, f)
+        L.zfp_field_free(f)
+        L.zfp_stream_close(z)
+        L.stream_close(bs)
+        return nbytes
+
     def compress(self, a, policy=0, threads=0, **mode):
         a = np.ascontiguousarray(a)
         words, _ = self.compress_raw(a.reshape(-1), 0, a.dtype, _shape_to_n(a.shape), None, mode,
