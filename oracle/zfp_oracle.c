@@ -201,6 +201,10 @@ static int64_t from_negabinary(uint64_t u, int P)
  * truncated at `budget` bits.  Returns the number of bits used (<= budget).  Covers
  * encode_few_ints, encode_many_ints and both *_prec variants: they differ only in whether the
  * budget can bind (src/template/codec.c:2-6). */
+/* optional coder statistics for kernel design work (planes visited, group-test runs, clusters of
+ * adjacent one-bits, verbatim bits); not part of the parity surface */
+uint64_t zo_stats[8];
+
 static unsigned encode_ints(sink* out, unsigned budget, unsigned maxprec, const uint64_t* u, unsigned size, unsigned intprec)
 {
   unsigned kmin = intprec > maxprec ? intprec - maxprec : 0;
@@ -212,6 +216,9 @@ static unsigned encode_ints(sink* out, unsigned budget, unsigned maxprec, const 
     out->limit = start + budget;
   for (k = intprec; k-- > kmin && out->pos - start < budget;) {
     /* bits of the n coefficients already known to be significant, verbatim */
+    zo_stats[0]++;
+    zo_stats[3] += n;
+    { unsigned j, any = 0; for (j = n; j < size; j++) any |= (unsigned)((u[j] >> k) & 1u); zo_stats[6] += any; }
     for (i = 0; i < n; i++)
       put_bit(out, (unsigned)((u[i] >> k) & 1u));
     /* the rest of the plane: "is there another one-bit?" then its distance in unary */
@@ -222,6 +229,12 @@ static unsigned encode_ints(sink* out, unsigned budget, unsigned maxprec, const 
       put_bit(out, next < size);
       if (next == size)
         break;
+      zo_stats[1]++;
+      if (next != n || n == 0 || !((u[n - 1] >> k) & 1u) ) {
+        zo_stats[2]++; /* a run that does not directly continue a previous one-bit starts a cluster */
+        if (next == n) zo_stats[4]++; /* ... with no zeros in front of it */
+        zo_stats[5] += next - n;
+      }
       for (; n < next; n++)
         put_bit(out, 0);
       if (n < size - 1)

@@ -17,8 +17,8 @@
 
 #include "../../include/zfp_b200_backend.h"
 #include "bitstream_impl.h"
-#include "kernels.cuh"
-#include "kernels4d.cuh"
+#include "types.h"
+#include "stream_kernels.cuh"
 
 using namespace zb;
 
@@ -203,81 +203,40 @@ extern "C" size_t zfp_b200_capacity(const zfp_b200_desc* d, uint64 start_bit)
 }
 
 // ------------------------------------------------------------------------------------------------
-// launches
+// launches: the kernel instances live in inst_{enc,dec}_<type>.cu
 // ------------------------------------------------------------------------------------------------
-template <int TYPE, int DIMS>
-static size_t plane_smem_bytes()
-{
-  constexpr int N = 1 << (2 * DIMS);
-  return (size_t)(kThreads / 32) * Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type);
-}
-
-template <class K>
-static bool allow_smem(K kernel, size_t bytes)
-{
-  return bytes <= 48 * 1024 ||
-         cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), "cudaFuncSetAttribute");
-}
-
-template <int TYPE, int DIMS, int OUT>
-static int launch_encode(const void* data, const Geom& g, const Params& prm, void* out, uint64_t start_bit,
-                         uint32_t slot_words, uint16_t* lengths, uint64_t b0, uint64_t b1, cudaStream_t st)
-{
-  auto kernel = encode_kernel<TYPE, DIMS, OUT>;
-  const size_t smem = plane_smem_bytes<TYPE, DIMS>();
-  if (!allow_smem(kernel, smem)) return ZFP_B200_ECUDA;
-  const uint64_t ctas = (b1 - b0 + kThreads - 1) / kThreads;
-  kernel<<<(unsigned)ctas, kThreads, smem, st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(data), g, prm, out,
-                                                  start_bit, slot_words, lengths, b0, b1);
-  LAUNCHED();
-  return ZFP_B200_OK;
-}
-
-template <int TYPE, int DIMS, int OFFS>
-static int launch_decode(void* data, const Geom& g, const Params& prm, const void* in, uint64_t start_bit,
-                         const uint64_t* offsets, cudaStream_t st)
-{
-  auto kernel = decode_kernel<TYPE, DIMS, OFFS>;
-  const size_t smem = plane_smem_bytes<TYPE, DIMS>();
-  if (!allow_smem(kernel, smem)) return ZFP_B200_ECUDA;
-  const uint64_t ctas = (g.nblocks + kThreads - 1) / kThreads;
-  kernel<<<(unsigned)ctas, kThreads, smem, st>>>(static_cast<typename Traits<TYPE>::Scalar*>(data), g, prm, in, start_bit, offsets);
-  LAUNCHED();
-  return ZFP_B200_OK;
-}
-
-// runtime (type, dims) -> template instance
-#define ZB_DISPATCH(FN, ...)                                                              \
-  switch (type * 10 + (int)dims) {                                                        \
-    case 11: return FN<T_INT32, 1, MODE>(__VA_ARGS__);                                    \
-    case 12: return FN<T_INT32, 2, MODE>(__VA_ARGS__);                                    \
-    case 13: return FN<T_INT32, 3, MODE>(__VA_ARGS__);                                    \
-    case 21: return FN<T_INT64, 1, MODE>(__VA_ARGS__);                                    \
-    case 22: return FN<T_INT64, 2, MODE>(__VA_ARGS__);                                    \
-    case 23: return FN<T_INT64, 3, MODE>(__VA_ARGS__);                                    \
-    case 31: return FN<T_FLOAT, 1, MODE>(__VA_ARGS__);                                    \
-    case 32: return FN<T_FLOAT, 2, MODE>(__VA_ARGS__);                                    \
-    case 33: return FN<T_FLOAT, 3, MODE>(__VA_ARGS__);                                    \
-    case 41: return FN<T_DOUBLE, 1, MODE>(__VA_ARGS__);                                   \
-    case 42: return FN<T_DOUBLE, 2, MODE>(__VA_ARGS__);                                   \
-    case 43: return FN<T_DOUBLE, 3, MODE>(__VA_ARGS__);                                   \
-    default: return ZFP_B200_EINVAL;                                                      \
-  }
-
-template <int MODE>
-static int encode_any(int type, uint32_t dims, const void* data, const Geom& g, const Params& prm, void* out,
+static int encode_any(int out_mode, int type, uint32_t dims, const void* data, const Geom& g, const Params& prm, void* out,
                       uint64_t start_bit, uint32_t slot_words, uint16_t* lengths, uint64_t b0, uint64_t b1, cudaStream_t st)
 {
-  if (dims == 4) return launch_encode4<MODE>(type, data, g, prm, out, start_bit, slot_words, lengths, b0, b1, st, g_launches);
-  ZB_DISPATCH(launch_encode, data, g, prm, out, start_bit, slot_words, lengths, b0, b1, st)
+  static const int staged = getenv("ZFP_B200_NO_STAGED") ? 0 : 1;
+  const EncodeArgs a = { data, g, prm, out, start_bit, slot_words, lengths, b0, b1, st, staged };
+  cudaError_t e;
+  switch (type) {
+    case T_INT32: e = launch_encode_t<T_INT32>((int)dims, out_mode, a); break;
+    case T_INT64: e = launch_encode_t<T_INT64>((int)dims, out_mode, a); break;
+    case T_FLOAT: e = launch_encode_t<T_FLOAT>((int)dims, out_mode, a); break;
+    case T_DOUBLE: e = launch_encode_t<T_DOUBLE>((int)dims, out_mode, a); break;
+    default: return ZFP_B200_EINVAL;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cuda_ok(e, "encode kernel launch") ? ZFP_B200_OK : ZFP_B200_ECUDA;
 }
 
-template <int MODE>
-static int decode_any(int type, uint32_t dims, void* data, const Geom& g, const Params& prm, const void* in,
+static int decode_any(int offs_mode, int type, uint32_t dims, void* data, const Geom& g, const Params& prm, const void* in,
                       uint64_t start_bit, const uint64_t* offsets, cudaStream_t st)
 {
-  if (dims == 4) return launch_decode4<MODE>(type, data, g, prm, in, start_bit, offsets, st, g_launches);
-  ZB_DISPATCH(launch_decode, data, g, prm, in, start_bit, offsets, st)
+  static const int staged = getenv("ZFP_B200_NO_STAGED") ? 0 : 1;
+  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, st, staged };
+  cudaError_t e;
+  switch (type) {
+    case T_INT32: e = launch_decode_t<T_INT32>((int)dims, offs_mode, a); break;
+    case T_INT64: e = launch_decode_t<T_INT64>((int)dims, offs_mode, a); break;
+    case T_FLOAT: e = launch_decode_t<T_FLOAT>((int)dims, offs_mode, a); break;
+    case T_DOUBLE: e = launch_decode_t<T_DOUBLE>((int)dims, offs_mode, a); break;
+    default: return ZFP_B200_EINVAL;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cuda_ok(e, "decode kernel launch") ? ZFP_B200_OK : ZFP_B200_ECUDA;
 }
 
 // exclusive scan of `n` block lengths into bit offsets, continuing at cursor[1]
@@ -317,14 +276,14 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
     // fixed rate: block b lives at start + b*maxbits, no communication between blocks
     const uint64_t total = g.nblocks * (uint64_t)d->maxbits, end = start_bit + total;
     if ((start_bit & 63) == 0 && (d->maxbits & 63) == 0)
-      rc = encode_any<0>(type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
+      rc = encode_any(0, type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
     else {
       uint64_t* w = static_cast<uint64_t*>(d_words);
       const uint64_t w0 = (start_bit + 63) >> 6, w1 = (end + 63) >> 6;
       clear_word_tail<<<1, 1, 0, st>>>(w, start_bit);
       LAUNCHED();
       if (w1 > w0) CU(cudaMemsetAsync(w + w0, 0, (w1 - w0) * 8, st));
-      rc = encode_any<1>(type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
+      rc = encode_any(1, type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
     }
     if (rc) return rc;
     if (end_bit) *end_bit = end;
@@ -358,7 +317,7 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
   LAUNCHED();
   for (uint64_t b0 = 0; b0 < g.nblocks; b0 += chunk) {
     const uint64_t b1 = b0 + chunk < g.nblocks ? b0 + chunk : g.nblocks, cn = b1 - b0;
-    rc = encode_any<2>(type, dims, d_data, g, prm, slots, 0, slot_words, lengths, b0, b1, st);
+    rc = encode_any(2, type, dims, d_data, g, prm, slots, 0, slot_words, lengths, b0, b1, st);
     if (rc) return rc;
     rc = scan_lengths(lengths + b0, cn, tiles, offsets, cursor, st);
     if (rc) return rc;
@@ -387,7 +346,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   int rc;
 
   if (d->minbits == d->maxbits) {
-    rc = decode_any<0>(d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, st);
+    rc = decode_any(0, d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, st);
     if (rc) return rc;
     if (end_bit) *end_bit = start_bit + g.nblocks * (uint64_t)d->maxbits;
     return ZFP_B200_OK;
@@ -405,7 +364,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   LAUNCHED();
   rc = scan_lengths(index->d_lengths, g.nblocks, tiles, offsets, cursor, st);
   if (rc) return rc;
-  rc = decode_any<1>(d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, st);
+  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, st);
   if (rc) return rc;
   uint64_t h_cursor[2];
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));

@@ -24,13 +24,10 @@
 #include <utility>
 #include <cuda_runtime.h>
 
+#include "types.h"
 #include "zfp_perm_tables.h"
 
 namespace zb {
-
-constexpr int kMinExp = -1074;  // ZFP_MIN_EXP
-
-enum : int { T_INT32 = 1, T_INT64 = 2, T_FLOAT = 3, T_DOUBLE = 4 };
 
 template <int TYPE> struct Traits;
 template <> struct Traits<T_INT32> {
@@ -54,23 +51,7 @@ template <> struct Traits<T_DOUBLE> {
   static constexpr bool is_fp = true;
 };
 
-struct Geom {
-  uint64_t n[4];    // extent per dimension (1 for unused)
-  int64_t s[4];     // element strides (resolved, never 0)
-  uint64_t nb[4];   // blocks per dimension
-  uint64_t nblocks;
-  int vec_rows;     // 1: sx == 1 and every 4-value row starts 16/32-byte aligned
-};
-
-struct Params {
-  uint32_t minbits, maxbits, maxprec;
-  int32_t minexp;
-};
-
-__constant__ uint8_t c_perm1[4] = ZFP_B200_PERM1_INIT;
-__constant__ uint8_t c_perm2[16] = ZFP_B200_PERM2_INIT;
-__constant__ uint8_t c_perm3[64] = ZFP_B200_PERM3_INIT;
-__constant__ uint8_t c_perm4[256] = ZFP_B200_PERM4_INIT;
+__constant__ uint8_t c_perm4[256] = ZFP_B200_PERM4_INIT;  // 4-D path only (kernels4d.cuh)
 
 // compile-time lookup (switch, no table in memory) so that reordering is pure register renaming
 // once the loops are unrolled
@@ -86,7 +67,13 @@ __host__ __device__ constexpr int perm_at(int i)
 // small bit helpers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t lowmask64(uint32_t n) { return n >= 64 ? ~0ull : ((1ull << n) - 1); }
-__device__ __forceinline__ uint32_t ctz64(uint64_t x) { return (uint32_t)__ffsll((long long)x) - 1; }
+// count trailing zeros of a non-zero 64-bit value with 32-bit operations
+__device__ __forceinline__ uint32_t ctz64(uint64_t x)
+{
+  const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  const uint32_t w = lo ? lo : hi;
+  return (uint32_t)__ffs((int)w) - 1 + (lo ? 0u : 32u);
+}
 
 // ------------------------------------------------------------------------------------------------
 // bit writer: LSB-first into 64-bit words (include/zfp/bitstream.inl:288-313 semantics).
@@ -97,6 +84,7 @@ __device__ __forceinline__ uint32_t ctz64(uint64_t x) { return (uint32_t)__ffsll
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 struct BitWriter {
+  static constexpr bool kStaged = false;
   unsigned long long* w;
   uint64_t acc;
   uint32_t fill;
@@ -138,8 +126,80 @@ struct BitWriter {
   }
 };
 
+// ------------------------------------------------------------------------------------------------
+// staged writer (fast fixed-rate path): the block's bits are assembled as 32-bit words in a
+// lane-private shared-memory column ([word][lane], bank = lane: conflict free whatever word each
+// lane is at) and copied out with wide stores by the kernel.  No per-append budget clamps: the
+// coder may overshoot by up to a plane; finish() drops everything at or beyond the block's bit
+// budget (word aligned in this mode), which is exactly the reference's truncation.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mask32(uint32_t len)  // low `len` bits set, 0 <= len <= 32
+{
+  uint32_t r;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(len));
+  return r;
+}
+
+struct StageWriter {
+  static constexpr bool kStaged = true;
+  uint32_t* p;   // next staging word of this lane (stride 32 words)
+  uint32_t* p0;
+  uint32_t lo, hi, fill;
+
+  __device__ __forceinline__ void init(uint32_t* column)
+  {
+    p = p0 = column;
+    lo = hi = 0;
+    fill = 0;
+  }
+  __device__ __forceinline__ void put32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
+  {
+    lo |= v << fill;
+    hi = __funnelshift_l(v, 0, fill);  // the part of v that does not fit the current word
+    fill += len;                       // <= 63
+    const uint32_t full = fill & 32;   // 32 when the current word is complete, else 0
+    if (full)
+      *p = lo;
+    p += full;                         // words of a lane are 32 elements apart
+    lo = full ? hi : lo;
+    fill &= 31;
+  }
+  __device__ __forceinline__ void put(uint64_t v, uint32_t len)  // len <= 64
+  {
+    if (len <= 32)
+      put32((uint32_t)v, len);
+    else {
+      put32((uint32_t)v, 32);
+      put32((uint32_t)(v >> 32), len - 32);
+    }
+  }
+  __device__ __forceinline__ void skip(uint32_t zeros)
+  {
+    fill += zeros;
+    while (fill >= 32) {
+      *p = lo;
+      p += 32;
+      lo = 0;
+      fill -= 32;
+    }
+  }
+  __device__ __forceinline__ void pad(uint32_t zeros) { skip(zeros); }
+  __device__ __forceinline__ uint32_t tell() const { return (uint32_t)(p - p0) + fill; }  // (p-p0)/32 words * 32 bits
+  // close the block at exactly total_words 32-bit words: flush, zero-fill, ignore overshoot
+  __device__ __forceinline__ void finish(uint32_t total_words)
+  {
+    if (fill) {
+      *p = lo;
+      p += 32;
+    }
+    for (uint32_t* q = p; q < p0 + 32 * total_words; q += 32)
+      *q = 0;
+  }
+};
+
 // bit reader with a 64-bit look-ahead window
 struct BitReader {
+  static constexpr bool kStaged = false;
   const uint64_t* w;  // next word to fetch
   uint64_t buf;       // unread bits, LSB first
   uint32_t avail;     // number of valid bits in buf (0..64)
@@ -183,6 +243,53 @@ struct BitReader {
     uint64_t v = peek(len);
     skip(len);
     return v;
+  }
+};
+
+// staged reader (fast fixed-rate path): the block's words were copied to a lane-private
+// shared-memory column ([word][lane]); a 64-bit window holds more than 32 valid bits at all
+// times so any read of <= 32 bits needs no refill check before it, only after.
+struct StageReader {
+  static constexpr bool kStaged = true;
+  const uint32_t* p;  // next word to fetch (stride 32 words)
+  uint32_t lo, hi;    // window, LSB first
+  uint32_t avail;     // valid bits in the window, 33..64 between calls
+
+  __device__ __forceinline__ void init(const uint32_t* column)
+  {
+    lo = column[0];
+    hi = column[32];
+    p = column + 64;
+    avail = 64;
+  }
+  __device__ __forceinline__ uint32_t peek32() const { return lo; }
+  __device__ __forceinline__ void skip32(uint32_t len)  // len <= 32
+  {
+    lo = __funnelshift_rc(lo, hi, len);
+    hi = __funnelshift_rc(hi, 0, len);
+    avail -= len;
+    if (avail <= 32) {
+      const uint32_t w = *p;
+      p += 32;
+      // append w at bit position avail (0..32)
+      lo |= avail < 32 ? w << avail : 0;
+      hi = __funnelshift_l(w, 0, avail) | (avail == 32 ? w : 0);
+      // for avail == 32 the word lands exactly in hi; funnelshift_l masks the shift to 0 there
+      avail += 32;
+    }
+  }
+  __device__ __forceinline__ uint32_t get32(uint32_t len)  // len <= 32
+  {
+    const uint32_t v = lo & mask32(len);
+    skip32(len);
+    return v;
+  }
+  __device__ __forceinline__ uint64_t get(uint32_t len)  // len <= 64
+  {
+    if (len <= 32)
+      return get32(len);
+    const uint32_t a = get32(32);
+    return (uint64_t)a | ((uint64_t)get32(len - 32) << 32);
   }
 };
 
@@ -280,9 +387,22 @@ __device__ __forceinline__ void transpose32_stage(uint32_t (&a)[32])
   for (int k = 0; k < 32; k++)
     if (!(k & J)) {
       // swap (row k, columns c+J) with (row k+J, columns c) for the columns c selected by m
-      uint32_t t = ((a[k] >> J) ^ a[k + J]) & m;
-      a[k + J] ^= t;
-      a[k] ^= t << J;
+      if (J == 16) {
+        // halfword granularity: two byte permutes instead of shift/xor/and
+        const uint32_t lo = __byte_perm(a[k], a[k + J], 0x5410), hi = __byte_perm(a[k], a[k + J], 0x7632);
+        a[k] = lo;
+        a[k + J] = hi;
+      }
+      else if (J == 8) {
+        const uint32_t lo = __byte_perm(a[k], a[k + J], 0x6240), hi = __byte_perm(a[k], a[k + J], 0x7351);
+        a[k] = lo;
+        a[k + J] = hi;
+      }
+      else {
+        uint32_t t = ((a[k] >> J) ^ a[k + J]) & m;
+        a[k + J] ^= t;
+        a[k] ^= t << J;
+      }
     }
 }
 
@@ -399,6 +519,69 @@ __device__ __forceinline__ uint32_t encode_planes(Writer& bw, uint32_t budget, u
   return budget - bits;
 }
 
+// Fast variant for the staged writer.  Uses two facts about the reference coder (encode.c:91-132):
+// the number n of coefficients coded verbatim in plane k is 1 + the highest coefficient index set
+// in any plane above k, and a one-bit that falls on the last coefficient is implied.
+//
+// The loop is flattened so that divergence between the 32 blocks of a warp costs little: every
+// iteration does the same work for every lane - (if the lane starts a new plane) fetch it and
+// append its n verbatim bits, then append ONE group-tested item: either the closing '0' test of a
+// plane without new coefficients, or one run ('1', z zeros, '1'; the last coefficient's one-bit is
+// implied), with the closing '0' folded in when it was the plane's last run.  Lanes whose planes
+// have several runs simply spend more iterations.  The bit budget is enforced by truncation in
+// StageWriter::finish().
+template <int N, int P>
+__device__ __forceinline__ uint32_t encode_planes_staged(StageWriter& bw, uint32_t budget, uint32_t maxprec,
+                                                         const typename PlaneWord<N>::type* sp)
+{
+  const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+  const uint32_t start = bw.tell();
+  uint64_t seen = 0;  // OR of the planes fetched so far
+  uint64_t r = 0;     // group-tested bits of the current plane still to code (bit 0 = coefficient pos)
+  uint32_t pos = 0;   // coefficients of the current plane settled so far
+  int k = P;
+  for (;;) {
+    uint32_t vlo = 0, vhi = 0, l1 = 0, l2 = 0;
+    bool fresh = false;
+    if (!r) {
+      // previous plane complete: fetch the next one
+      if (--k < kmin || bw.tell() - start >= budget)
+        break;
+      const uint64_t x = sp[k * 32];
+      const uint32_t n = seen ? 64 - (uint32_t)__clzll((long long)seen) : 0;  // <= N
+      seen |= x;
+      l1 = n < 32 ? n : 32;
+      l2 = n - l1;
+      vlo = (uint32_t)x & mask32(l1);
+      vhi = (uint32_t)(x >> 32) & mask32(l2);
+      r = n < 64 ? x >> n : 0;
+      pos = n;
+      fresh = true;
+    }
+    bw.put32(vlo, l1);
+    bw.put32(vhi, l2);
+    if (r) {
+      const uint32_t z = ctz64(r);  // zeros before the next one-bit
+      pos += z + 1;
+      r = z < 63 ? r >> (z + 1) : 0;
+      const uint32_t explicit_one = pos < N ? 1u : 0u;
+      // the plane's closing '0' test rides along (as an extra zero bit) when this was its last run
+      const uint32_t closing = (!r && pos < N) ? 1u : 0u;
+      if (z < 29)
+        bw.put32(1u | (explicit_one << (z + 1)), z + 1 + explicit_one + closing);
+      else {
+        bw.put32(1, 1);
+        bw.skip(z);
+        bw.put32(explicit_one, explicit_one + closing);
+      }
+    }
+    else if (fresh)
+      bw.put32(0, pos < N ? 1u : 0u);  // no new coefficient in this plane: just the '0' test
+  }
+  const uint32_t used = bw.tell() - start;
+  return used < budget ? used : budget;
+}
+
 // Mirror image.  Decoded planes are stored to sp[k*32]; returns bits consumed and, through
 // kstop, the lowest plane index that was written.
 template <int N, int P>
@@ -431,6 +614,123 @@ __device__ __forceinline__ uint32_t decode_planes(BitReader& br, uint32_t budget
     sp[k * 32] = (typename PlaneWord<N>::type)x;
   }
   kstop = k + 1;
+  return budget - bits;
+}
+
+// Group-tested part of one plane with exact budget accounting, one bit at a time (the reference's
+// loop, decode.c:96-117, including its deposit-on-exhaustion rule).  Used where the budget may bind.
+template <int N, class Reader>
+__device__ __forceinline__ void decode_group_exact(Reader& br, uint32_t& bits, uint32_t& n, uint64_t& x)
+{
+  while (bits && n < N) {
+    bits--;
+    if (!br.get32(1))
+      break;
+    while (bits && n < N - 1) {
+      bits--;
+      if (br.get32(1))
+        break;
+      n++;
+    }
+    x |= 1ull << n;
+    n++;
+  }
+}
+
+// Fast variant for the staged reader: the mirror image of encode_planes_staged, flattened the same
+// way (per iteration: optionally start a plane by reading its verbatim bits, then decode one
+// group-tested item).  Budget accounting is exact at every step, including the reference's
+// deposit-on-exhaustion rule (decode.c:103-111): a run is limited to min(bits left, N-1-n) zeros
+// and the one-bit is deposited where the scan stopped.
+template <int N, int P>
+__device__ __forceinline__ uint32_t decode_planes_staged(StageReader& br, uint32_t budget, uint32_t maxprec,
+                                                         typename PlaneWord<N>::type* sp, int& kstop)
+{
+  const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+  uint32_t bits = budget, n = 0;
+  uint64_t x = 0;
+  bool open = false;  // a plane is in progress (its next item starts with a group test)
+  int k = P, lowest = P;
+  for (;;) {
+    if (!open) {
+      if (!bits || --k < kmin)
+        break;
+      const uint32_t m = n < bits ? n : bits;
+      const uint32_t l1 = m < 32 ? m : 32, l2 = m - l1;
+      x = br.get32(l1);
+      x |= (uint64_t)br.get32(l2) << 32;
+      bits -= m;
+      open = true;
+    }
+    bool done = true;
+    if (bits && n < N) {
+      const uint32_t g = br.peek32();
+      if (g & 1u) {
+        // positive group test: zeros up to the next one-bit, the last coefficient or the budget
+        const uint32_t avail = bits - 1;
+        const uint32_t room = N - 1 - n;
+        const uint32_t lim = avail < room ? avail : room;
+        const bool found = (g >> 1) != 0;  // a one-bit is visible among the next 31 bits
+        const uint32_t z = found ? (uint32_t)__ffs((int)(g >> 1)) - 1 : 31u;
+        if (found && z < lim) {
+          br.skip32(z + 2);  // test, z zeros, one
+          bits -= z + 2;
+          n += z;
+        }
+        else if (lim <= 31) {
+          br.skip32(lim + 1);  // test and lim zeros; the one-bit is implied / the budget ran out
+          bits -= lim + 1;
+          n += lim;
+        }
+        else {
+          // more than 31 zeros in a row: keep scanning a window at a time
+          br.skip32(32);
+          bits -= 32;
+          n += 31;
+          uint32_t left = lim - 31;
+          for (;;) {
+            const uint32_t w = br.peek32();
+            const uint32_t step = left < 32 ? left : 32;
+            const uint32_t zz = w ? (uint32_t)__ffs((int)w) - 1 : 32u;
+            if (zz < step) {
+              br.skip32(zz + 1);
+              bits -= zz + 1;
+              n += zz;
+              break;
+            }
+            br.skip32(step);
+            bits -= step;
+            n += step;
+            left -= step;
+            if (!left)
+              break;
+          }
+        }
+        x |= 1ull << n;
+        n++;
+        // the plane goes on if coefficients and budget remain and the next test is positive;
+        // a negative test closes it and is consumed here
+        if (bits && n < N) {
+          if (br.peek32() & 1u)
+            done = false;
+          else {
+            br.skip32(1);
+            bits--;
+          }
+        }
+      }
+      else {
+        br.skip32(1);
+        bits--;
+      }
+    }
+    if (done) {
+      sp[k * 32] = (typename PlaneWord<N>::type)x;
+      lowest = k;
+      open = false;
+    }
+  }
+  kstop = lowest;
   return budget - bits;
 }
 
@@ -545,7 +845,7 @@ __device__ __forceinline__ typename std::make_signed<UInt>::type uint2int(UInt u
 // whole-block encode / decode for one thread.  `sp` is the lane's plane column in shared memory.
 // Returns the number of bits the block occupies in the stream.
 // ------------------------------------------------------------------------------------------------
-template <int TYPE, int DIMS, class Writer>
+template <int TYPE, int DIMS, bool REV, class Writer>
 __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Scalar (&v)[1 << (2 * DIMS)],
                                                  const Params& prm, Writer& bw,
                                                  typename PlaneWord<(1 << (2 * DIMS))>::type* sp)
@@ -554,7 +854,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   using Int = typename TR::Int;
   using UInt = typename TR::UInt;
   constexpr int N = 1 << (2 * DIMS), P = TR::P;
-  const bool reversible = prm.minexp < kMinExp;
+  constexpr bool reversible = REV;  // prm.minexp < ZFP_MIN_EXP, resolved by the launcher
   uint32_t bits = 0, maxprec = prm.maxprec;
   Int q[N];
 
@@ -643,7 +943,10 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     maxprec = prec;
   }
   to_planes<UInt, N>(u, sp);
-  bits += encode_planes<N, P>(bw, prm.maxbits - bits, maxprec, sp);
+  if constexpr (Writer::kStaged)
+    bits += encode_planes_staged<N, P>(bw, prm.maxbits - bits, maxprec, sp);
+  else
+    bits += encode_planes<N, P>(bw, prm.maxbits - bits, maxprec, sp);
   if (bits < prm.minbits) {
     bw.pad(prm.minbits - bits);
     bits = prm.minbits;
@@ -651,9 +954,9 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   return bits;
 }
 
-template <int TYPE, int DIMS>
+template <int TYPE, int DIMS, bool REV, class Reader>
 __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (&v)[1 << (2 * DIMS)],
-                                                 const Params& prm, BitReader& br,
+                                                 const Params& prm, Reader& br,
                                                  typename PlaneWord<(1 << (2 * DIMS))>::type* sp)
 {
   using TR = Traits<TYPE>;
@@ -661,7 +964,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   using Int = typename TR::Int;
   using UInt = typename TR::UInt;
   constexpr int N = 1 << (2 * DIMS), P = TR::P;
-  const bool reversible = prm.minexp < kMinExp;
+  constexpr bool reversible = REV;  // prm.minexp < ZFP_MIN_EXP, resolved by the launcher
   uint32_t bits = 0, maxprec = prm.maxprec;
   int emax = 0;
   bool reinterpret = false;
@@ -694,7 +997,10 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   }
 
   int kstop;
-  bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
+  if constexpr (Reader::kStaged)
+    bits += decode_planes_staged<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
+  else
+    bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
   if (bits < prm.minbits)
     bits = prm.minbits;
 

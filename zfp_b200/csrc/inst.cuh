@@ -1,0 +1,150 @@
+// inst.cuh - launchers: runtime (dims, output mode, reversible) -> kernel template instance.
+// Included by one translation unit per scalar type and direction (inst_<dir>_<type>.cu) so the
+// 100+ kernel instances compile in parallel.
+#pragma once
+
+#include "kernels.cuh"
+#include "kernels4d.cuh"
+
+namespace zb {
+
+constexpr uint32_t kStagedMaxBits = 4096;  // staging stays under ~17 KiB per warp
+
+template <int TYPE, int DIMS>
+constexpr size_t plane_smem_bytes()
+{
+  constexpr int N = 1 << (2 * DIMS);
+  return (size_t)(kThreads / 32) * Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type);
+}
+
+template <class K>
+inline cudaError_t allow_smem(K kernel, size_t bytes)
+{
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+
+template <int TYPE, int DIMS, bool REV>
+cudaError_t run_encode_staged(const EncodeArgs& a)
+{
+  constexpr int N = 1 << (2 * DIMS);
+  auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
+  const size_t smem = (size_t)(kThreads / 32) * (Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type) +
+                                                 ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4);
+  static size_t allowed = 0;  // per kernel instance
+  if (smem > 48 * 1024 && smem > allowed) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    allowed = smem;
+  }
+  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
+  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                    static_cast<uint64_t*>(a.out), a.start_bit);
+  return cudaGetLastError();
+}
+
+template <int TYPE, int DIMS, int OUT, bool REV>
+cudaError_t run_encode(const EncodeArgs& a)
+{
+  if constexpr (OUT == 0)
+    if (a.staged && a.prm.maxbits <= kStagedMaxBits && a.b0 == 0 && a.b1 == a.g.nblocks)
+      return run_encode_staged<TYPE, DIMS, REV>(a);
+  auto kernel = encode_kernel<TYPE, DIMS, OUT, REV>;
+  constexpr size_t smem = plane_smem_bytes<TYPE, DIMS>();
+  cudaError_t e = allow_smem(kernel, smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;
+  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.out,
+                                                    a.start_bit, a.slot_words, a.lengths, a.b0, a.b1);
+  return cudaGetLastError();
+}
+
+template <int TYPE, int DIMS, bool REV>
+cudaError_t run_decode_staged(const DecodeArgs& a)
+{
+  constexpr int N = 1 << (2 * DIMS);
+  auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
+  const size_t smem = (size_t)(kThreads / 32) * (Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type) +
+                                                 ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4);
+  static size_t allowed = 0;
+  if (smem > 48 * 1024 && smem > allowed) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    allowed = smem;
+  }
+  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
+  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                    static_cast<const uint64_t*>(a.in), a.start_bit);
+  return cudaGetLastError();
+}
+
+template <int TYPE, int DIMS, int OFFS, bool REV>
+cudaError_t run_decode(const DecodeArgs& a)
+{
+  if constexpr (OFFS == 0)
+    if (a.staged && a.prm.maxbits <= kStagedMaxBits && (a.prm.maxbits & 63) == 0 && (a.start_bit & 63) == 0)
+      return run_decode_staged<TYPE, DIMS, REV>(a);
+  auto kernel = decode_kernel<TYPE, DIMS, OFFS, REV>;
+  constexpr size_t smem = plane_smem_bytes<TYPE, DIMS>();
+  cudaError_t e = allow_smem(kernel, smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
+  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
+                                                    a.start_bit, a.offsets);
+  return cudaGetLastError();
+}
+
+template <int TYPE, int OUT>
+cudaError_t run_encode4(const EncodeArgs& a)
+{
+  const unsigned ctas = (unsigned)((a.b1 - a.b0 + kThreads4 - 1) / kThreads4);
+  encode4_kernel<TYPE, OUT><<<ctas, kThreads4, 0, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                           a.out, a.start_bit, a.slot_words, a.lengths, a.b0, a.b1);
+  return cudaGetLastError();
+}
+
+template <int TYPE, int OFFS>
+cudaError_t run_decode4(const DecodeArgs& a)
+{
+  const unsigned ctas = (unsigned)((a.g.nblocks + kThreads4 - 1) / kThreads4);
+  decode4_kernel<TYPE, OFFS><<<ctas, kThreads4, 0, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
+                                                            a.start_bit, a.offsets);
+  return cudaGetLastError();
+}
+
+#define ZB_ENC_CASE(D, O)                                                     \
+  case (D) * 10 + (O): return rev ? run_encode<TYPE, D, O, true>(a) : run_encode<TYPE, D, O, false>(a);
+#define ZB_DEC_CASE(D, O)                                                     \
+  case (D) * 10 + (O): return rev ? run_decode<TYPE, D, O, true>(a) : run_decode<TYPE, D, O, false>(a);
+
+template <int TYPE>
+cudaError_t launch_encode_impl(int dims, int out_mode, const EncodeArgs& a)
+{
+  const bool rev = a.prm.minexp < kMinExp;
+  switch (dims * 10 + out_mode) {
+    ZB_ENC_CASE(1, 0) ZB_ENC_CASE(1, 1) ZB_ENC_CASE(1, 2)
+    ZB_ENC_CASE(2, 0) ZB_ENC_CASE(2, 1) ZB_ENC_CASE(2, 2)
+    ZB_ENC_CASE(3, 0) ZB_ENC_CASE(3, 1) ZB_ENC_CASE(3, 2)
+    case 40: return run_encode4<TYPE, 0>(a);
+    case 41: return run_encode4<TYPE, 1>(a);
+    case 42: return run_encode4<TYPE, 2>(a);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int TYPE>
+cudaError_t launch_decode_impl(int dims, int offs_mode, const DecodeArgs& a)
+{
+  const bool rev = a.prm.minexp < kMinExp;
+  switch (dims * 10 + offs_mode) {
+    ZB_DEC_CASE(1, 0) ZB_DEC_CASE(1, 1)
+    ZB_DEC_CASE(2, 0) ZB_DEC_CASE(2, 1)
+    ZB_DEC_CASE(3, 0) ZB_DEC_CASE(3, 1)
+    case 40: return run_decode4<TYPE, 0>(a);
+    case 41: return run_decode4<TYPE, 1>(a);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace zb

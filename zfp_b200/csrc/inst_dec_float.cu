@@ -1,0 +1,5 @@
+// decode kernels for float (all dims, offset modes, lossy + reversible)
+#include "inst.cuh"
+namespace zb {
+template <> cudaError_t launch_decode_t<3>(int dims, int offs_mode, const DecodeArgs& a) { return launch_decode_impl<3>(dims, offs_mode, a); }
+}

@@ -1,0 +1,5 @@
+// encode kernels for double (all dims, output modes, lossy + reversible)
+#include "inst.cuh"
+namespace zb {
+template <> cudaError_t launch_encode_t<4>(int dims, int out_mode, const EncodeArgs& a) { return launch_encode_impl<4>(dims, out_mode, a); }
+}

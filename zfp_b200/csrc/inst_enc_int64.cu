@@ -1,0 +1,5 @@
+// encode kernels for int64 (all dims, output modes, lossy + reversible)
+#include "inst.cuh"
+namespace zb {
+template <> cudaError_t launch_encode_t<2>(int dims, int out_mode, const EncodeArgs& a) { return launch_encode_impl<2>(dims, out_mode, a); }
+}

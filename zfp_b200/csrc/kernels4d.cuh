@@ -8,8 +8,6 @@
 // transform axis order x,y,z,w (encode4.c fwd_xform) and w,z,y,x for the inverse.
 #pragma once
 
-#include <atomic>
-
 #include "kernels.cuh"
 
 namespace zb {
@@ -410,39 +408,6 @@ decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params 
         v[i] = (Scalar)q[i];
   }
   scatter4(v, data, g, locate4(g, b));
-}
-
-template <int OUT>
-static int launch_encode4(int type, const void* data, const Geom& g, const Params& prm, void* out, uint64_t start_bit,
-                          uint32_t slot_words, uint16_t* lengths, uint64_t b0, uint64_t b1, cudaStream_t st,
-                          std::atomic<uint64_t>& launches)
-{
-  const unsigned ctas = (unsigned)((b1 - b0 + kThreads4 - 1) / kThreads4);
-  switch (type) {
-    case T_INT32: encode4_kernel<T_INT32, OUT><<<ctas, kThreads4, 0, st>>>((const int32_t*)data, g, prm, out, start_bit, slot_words, lengths, b0, b1); break;
-    case T_INT64: encode4_kernel<T_INT64, OUT><<<ctas, kThreads4, 0, st>>>((const int64_t*)data, g, prm, out, start_bit, slot_words, lengths, b0, b1); break;
-    case T_FLOAT: encode4_kernel<T_FLOAT, OUT><<<ctas, kThreads4, 0, st>>>((const float*)data, g, prm, out, start_bit, slot_words, lengths, b0, b1); break;
-    case T_DOUBLE: encode4_kernel<T_DOUBLE, OUT><<<ctas, kThreads4, 0, st>>>((const double*)data, g, prm, out, start_bit, slot_words, lengths, b0, b1); break;
-    default: return 1;
-  }
-  launches.fetch_add(1);
-  return cudaGetLastError() == cudaSuccess ? 0 : 2;
-}
-
-template <int OFFS>
-static int launch_decode4(int type, void* data, const Geom& g, const Params& prm, const void* in, uint64_t start_bit,
-                          const uint64_t* offsets, cudaStream_t st, std::atomic<uint64_t>& launches)
-{
-  const unsigned ctas = (unsigned)((g.nblocks + kThreads4 - 1) / kThreads4);
-  switch (type) {
-    case T_INT32: decode4_kernel<T_INT32, OFFS><<<ctas, kThreads4, 0, st>>>((int32_t*)data, g, prm, in, start_bit, offsets); break;
-    case T_INT64: decode4_kernel<T_INT64, OFFS><<<ctas, kThreads4, 0, st>>>((int64_t*)data, g, prm, in, start_bit, offsets); break;
-    case T_FLOAT: decode4_kernel<T_FLOAT, OFFS><<<ctas, kThreads4, 0, st>>>((float*)data, g, prm, in, start_bit, offsets); break;
-    case T_DOUBLE: decode4_kernel<T_DOUBLE, OFFS><<<ctas, kThreads4, 0, st>>>((double*)data, g, prm, in, start_bit, offsets); break;
-    default: return 1;
-  }
-  launches.fetch_add(1);
-  return cudaGetLastError() == cudaSuccess ? 0 : 2;
 }
 
 }  // namespace zb

@@ -1,0 +1,141 @@
+// stream_kernels.cuh - block-length scan and bit-granular stream assembly (variable-rate modes).
+#pragma once
+
+#include "codec.cuh"
+
+namespace zb {
+
+// ------------------------------------------------------------------------------------------------
+// block-length scan (exclusive prefix of 16-bit lengths into 64-bit bit offsets)
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 16;
+constexpr int kScanTile = kScanThreads * kScanPerThread;  // 4096 blocks per tile
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
+{
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) >= d) v += t;
+  }
+  return v;
+}
+
+// exclusive scan across the CTA of one uint32 per thread; returns the exclusive prefix and the total
+__device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t& total)
+{
+  __shared__ uint32_t ws[33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const uint32_t incl = warp_incl_scan(v);
+  __syncthreads();  // readers of the previous call are done with ws
+  if (lane == 31) ws[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = lane < nw ? ws[lane] : 0;
+    uint32_t si = warp_incl_scan(s);
+    ws[lane] = si - s;
+    if (lane == 31) ws[32] = si;
+  }
+  __syncthreads();
+  total = ws[32];
+  return ws[wid] + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sums(const uint16_t* __restrict__ lengths, uint64_t n, uint64_t* __restrict__ tile_sum)
+{
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; i++)
+    s += base + i < n ? lengths[base + i] : 0u;
+  uint32_t total;
+  cta_excl_scan(s, total);
+  if (threadIdx.x == 0)
+    tile_sum[blockIdx.x] = total;
+}
+
+// single CTA: exclusive scan of the tile sums, starting at cursor[1]; cursor <- {begin, end}
+__global__ void __launch_bounds__(1024)
+scan_tile_offsets(uint64_t* __restrict__ tile_sum, uint64_t ntiles, uint64_t* __restrict__ cursor)
+{
+  __shared__ uint64_t carry;
+  if (threadIdx.x == 0) { carry = cursor[1]; cursor[0] = cursor[1]; }
+  __syncthreads();
+  for (uint64_t t0 = 0; t0 < ntiles; t0 += blockDim.x) {
+    uint64_t i = t0 + threadIdx.x;
+    uint64_t v = i < ntiles ? tile_sum[i] : 0;
+    // tile sums fit 32 bits (4096 * 16658), their running total does not: scan 32-bit, carry 64-bit
+    uint32_t total;
+    uint32_t excl = cta_excl_scan((uint32_t)v, total);
+    if (i < ntiles)
+      tile_sum[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cursor[1] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply(const uint16_t* __restrict__ lengths, uint64_t n, const uint64_t* __restrict__ tile_off,
+           uint64_t* __restrict__ offsets)
+{
+  const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
+  uint32_t len[kScanPerThread], s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; i++) {
+    len[i] = base + i < n ? lengths[base + i] : 0u;
+    s += len[i];
+  }
+  uint32_t total;
+  uint64_t o = tile_off[blockIdx.x] + cta_excl_scan(s, total);
+#pragma unroll
+  for (int i = 0; i < kScanPerThread; i++) {
+    if (base + i < n) offsets[base + i] = o;
+    o += len[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stream assembly helpers
+// ------------------------------------------------------------------------------------------------
+
+// clear bits >= (bit % 64) of the word holding `bit` (keeps a header written before the payload)
+__global__ void clear_word_tail(uint64_t* words, uint64_t bit)
+{
+  if (bit & 63)
+    words[bit >> 6] &= (1ull << (bit & 63)) - 1;
+}
+
+// zero the words that start inside [cursor[0], cursor[1]) (device-side bounds)
+__global__ void zero_new_words(uint64_t* __restrict__ words, const uint64_t* __restrict__ cursor)
+{
+  const uint64_t w0 = (cursor[0] + 63) >> 6, w1 = (cursor[1] + 63) >> 6;
+  for (uint64_t i = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < w1; i += (uint64_t)gridDim.x * blockDim.x)
+    words[i] = 0;
+}
+
+// concatenate the coded blocks of a chunk: block b's bits move from its scratch slot to its bit
+// offset in the stream (stream_copy semantics, include/zfp/bitstream.inl:412-424)
+__global__ void __launch_bounds__(256)
+compact_blocks(const uint64_t* __restrict__ scratch, uint32_t slot_words, const uint16_t* __restrict__ lengths,
+               const uint64_t* __restrict__ offsets, uint64_t nblocks, void* __restrict__ out)
+{
+  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks)
+    return;
+  const uint64_t* src = scratch + b * slot_words;
+  uint32_t len = lengths[b];
+  BitWriter<1> bw;
+  bw.init(out, offsets[b]);
+  for (uint32_t i = 0; len; i++) {
+    uint32_t c = len < 64 ? len : 64;
+    bw.put(src[i] & lowmask64(c), c);
+    len -= c;
+  }
+  bw.flush();
+}
+
+}  // namespace zb

@@ -1,0 +1,57 @@
+// types.h - plain structs shared by the host dispatch and the kernel translation units.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zb {
+
+constexpr int kMinExp = -1074;  // ZFP_MIN_EXP
+
+enum : int { T_INT32 = 1, T_INT64 = 2, T_FLOAT = 3, T_DOUBLE = 4 };  // zfp_type numbering
+
+struct Geom {
+  uint64_t n[4];    // extent per dimension (1 for unused)
+  int64_t s[4];     // element strides (resolved, never 0)
+  uint64_t nb[4];   // blocks per dimension
+  uint64_t nblocks;
+  int vec_rows;     // 1: sx == 1 and every 4-value row starts 16/32-byte aligned
+};
+
+struct Params {
+  uint32_t minbits, maxbits, maxprec;
+  int32_t minexp;
+};
+
+// OUT: 0 fixed rate, word-aligned blocks (plain stores); 1 fixed rate, blocks share words
+// (OR-merge into a zeroed destination); 2 variable rate (scratch slot per block + length)
+struct EncodeArgs {
+  const void* data;
+  Geom g;
+  Params prm;
+  void* out;
+  uint64_t start_bit;
+  uint32_t slot_words;
+  uint16_t* lengths;
+  uint64_t b0, b1;  // block range [b0, b1)
+  cudaStream_t st;
+  int staged;       // OUT 0 only: use the shared-memory staged fast path
+};
+
+// OFFS: 0 fixed rate (offset = start + b*maxbits), 1 per-block offsets from the index scan
+struct DecodeArgs {
+  void* data;
+  Geom g;
+  Params prm;
+  const void* in;
+  uint64_t start_bit;
+  const uint64_t* offsets;
+  cudaStream_t st;
+  int staged;       // OFFS 0 only: use the shared-memory staged fast path when the stream is word aligned
+};
+
+// one translation unit per scalar type and direction (inst_*.cu) defines these
+template <int TYPE> cudaError_t launch_encode_t(int dims, int out_mode, const EncodeArgs& a);
+template <int TYPE> cudaError_t launch_decode_t(int dims, int offs_mode, const DecodeArgs& a);
+
+}  // namespace zb
