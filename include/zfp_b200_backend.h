@@ -84,6 +84,12 @@ int zfp_b200_encode(const zfp_b200_desc* desc, const void* d_data, void* d_words
 int zfp_b200_decode(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
                     uint64* end_bit, const zfp_b200_index* index, void* cuda_stream);
 
+/* Bit-granular device copy dst[dst_bit, dst_bit+nbits) = src[src_bit, ...): places a slab stream
+ * produced at another bit phase / on another GPU into a global stream.  Destination words fully
+ * inside the range are overwritten, partially covered ones OR-merged (their target bits must be 0). */
+int zfp_b200_bitcopy(void* d_dst_words, uint64 dst_bit, const void* d_src_words, uint64 src_bit, uint64 nbits,
+                     void* cuda_stream);
+
 /* 1 if the parameters make every block the same size (minbits == maxbits) */
 int zfp_b200_is_fixed_rate(const zfp_b200_desc* desc);
 /* number of 4^d blocks in the field */

@@ -85,6 +85,7 @@ _PROTOTYPES = {
     "zfp_stream_cuda_params": (C.POINTER(CudaParams), [_vp]),
     "zfp_b200_encode": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp]),
     "zfp_b200_decode": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp]),
+    "zfp_b200_bitcopy": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]),
     "zfp_b200_is_fixed_rate": (C.c_int, [C.POINTER(Desc)]), "zfp_b200_blocks": (_sz, [C.POINTER(Desc)]),
     "zfp_b200_capacity": (_sz, [C.POINTER(Desc), C.c_uint64]),
     "zfp_b200_index_create": (_vp, []), "zfp_b200_index_destroy": (None, [_vp]),
@@ -139,6 +140,32 @@ def _set_mode(L, z, mode, zfp_type, dims):
             raise ValueError("invalid expert parameters %r" % (mode["expert"],))
     else:
         raise ValueError("no compression mode given: %r" % (mode,))
+
+
+def mode_params(mode, dtype_name, dims):
+    """(minbits, maxbits, maxprec, minexp) the library derives for a mode (no GPU needed)."""
+    L = load_library()
+    z = L.zfp_stream_open(None)
+    _set_mode(L, z, mode, ZFP_TYPE[str(dtype_name).replace("torch.", "")], dims)
+    v = [C.c_uint(), C.c_uint(), C.c_uint(), C.c_int()]
+    L.zfp_stream_params(z, *[C.byref(x) for x in v])
+    L.zfp_stream_close(z)
+    return tuple(x.value for x in v)
+
+
+def is_fixed_rate_mode(mode):
+    if mode.get("rate") is not None:
+        return True
+    if mode.get("expert") is not None:
+        return mode["expert"][0] == mode["expert"][1]
+    return False
+
+
+def bitcopy(dst_words, dst_bit, src_words, src_bit, nbits, cuda_stream=None):
+    """Device bit-granular copy between two int64 CUDA tensors of stream words."""
+    rc = load_library().zfp_b200_bitcopy(dst_words.data_ptr(), dst_bit, src_words.data_ptr(), src_bit, nbits, cuda_stream)
+    if rc:
+        raise RuntimeError("zfp_b200_bitcopy failed: %s" % last_error())
 
 
 def _make_field(L, ptr, zfp_type, shape, strides):

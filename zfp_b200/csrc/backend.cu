@@ -352,9 +352,28 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
     return ZFP_B200_OK;
   }
 
-  if (!index || index->blocks != g.nblocks) {
-    g_error = "zfp_b200_decode: variable-rate stream needs a block index with one entry per block";
+  const uint16_t* lengths;
+  if (index && index->blocks == g.nblocks)
+    lengths = index->d_lengths;
+  else if (index && index->blocks) {
+    g_error = "zfp_b200_decode: block index does not match the field (wrong number of blocks)";
     return ZFP_B200_ENOINDEX;
+  }
+  else {
+    // foreign stream: rebuild the index by parsing the stream sequentially on the device
+    uint16_t* rebuilt = static_cast<uint16_t*>(scratch(SCR_LENGTHS, g.nblocks * sizeof(uint16_t)));
+    if (!rebuilt) return ZFP_B200_ECUDA;
+    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, st, 0 };
+    cudaError_t e;
+    switch (d->type) {
+      case T_INT32: e = launch_index_t<T_INT32>((int)d->dims, a, rebuilt); break;
+      case T_INT64: e = launch_index_t<T_INT64>((int)d->dims, a, rebuilt); break;
+      case T_FLOAT: e = launch_index_t<T_FLOAT>((int)d->dims, a, rebuilt); break;
+      default: e = launch_index_t<T_DOUBLE>((int)d->dims, a, rebuilt); break;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!cuda_ok(e, "index scan launch")) return ZFP_B200_ECUDA;
+    lengths = rebuilt;
   }
   uint64_t* tiles = static_cast<uint64_t*>(scratch(SCR_TILES, ((g.nblocks + kScanTile - 1) / kScanTile + 1) * 8));
   uint64_t* offsets = static_cast<uint64_t*>(scratch(SCR_OFFSETS, g.nblocks * 8));
@@ -362,7 +381,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   if (!tiles || !offsets || !cursor) return ZFP_B200_ECUDA;
   set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
   LAUNCHED();
-  rc = scan_lengths(index->d_lengths, g.nblocks, tiles, offsets, cursor, st);
+  rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st);
   if (rc) return rc;
   rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, st);
   if (rc) return rc;
@@ -370,6 +389,20 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (end_bit) *end_bit = h_cursor[1];
+  return ZFP_B200_OK;
+}
+
+extern "C" int zfp_b200_bitcopy(void* d_dst_words, uint64 dst_bit, const void* d_src_words, uint64 src_bit, uint64 nbits,
+                                void* cuda_stream)
+{
+  if (!nbits) return ZFP_B200_OK;
+  if (!d_dst_words || !d_src_words) return ZFP_B200_EINVAL;
+  const uint64_t words = ((dst_bit + nbits + 63) >> 6) - (dst_bit >> 6);
+  unsigned ctas = (unsigned)((words + 255) / 256);
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  bitcopy_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<uint64_t*>(d_dst_words), dst_bit,
+                                                                           static_cast<const uint64_t*>(d_src_words), src_bit, nbits);
+  LAUNCHED();
   return ZFP_B200_OK;
 }
 

@@ -147,4 +147,21 @@ cudaError_t launch_decode_impl(int dims, int offs_mode, const DecodeArgs& a)
   }
 }
 
+template <int TYPE>
+cudaError_t launch_index_impl(int dims, const DecodeArgs& a, uint16_t* lengths)
+{
+  const bool rev = a.prm.minexp < kMinExp;
+  switch (dims) {
+    case 1: if (rev) index_scan_kernel<TYPE, 1, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths);
+            else index_scan_kernel<TYPE, 1, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
+    case 2: if (rev) index_scan_kernel<TYPE, 2, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths);
+            else index_scan_kernel<TYPE, 2, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
+    case 3: if (rev) index_scan_kernel<TYPE, 3, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths);
+            else index_scan_kernel<TYPE, 3, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
+    case 4: index_scan4_kernel<TYPE><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace zb

@@ -2,4 +2,5 @@
 #include "inst.cuh"
 namespace zb {
 template <> cudaError_t launch_decode_t<2>(int dims, int offs_mode, const DecodeArgs& a) { return launch_decode_impl<2>(dims, offs_mode, a); }
+template <> cudaError_t launch_index_t<2>(int dims, const DecodeArgs& a, uint16_t* lengths) { return launch_index_impl<2>(dims, a, lengths); }
 }

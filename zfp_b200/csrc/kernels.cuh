@@ -296,4 +296,27 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   scatter<DIMS>(v, data, g, pos);
 }
 
+// Index rebuild for a variable-rate stream that arrives without block lengths: block b's position
+// is only known once blocks 0..b-1 have been parsed (the zfp format stores no offsets,
+// docs/source/execution.rst:292-300), so this is inherently sequential: ONE thread walks the stream.
+// Correct but slow; streams produced by this backend carry their index and never come here.
+template <int TYPE, int DIMS, bool REV>
+__global__ void index_scan_kernel(const void* __restrict__ in, uint64_t start_bit, uint64_t nblocks, Params prm,
+                                  uint16_t* __restrict__ lengths)
+{
+  using TR = Traits<TYPE>;
+  constexpr int N = 1 << (2 * DIMS);
+  using PW = typename PlaneWord<N>::type;
+  __shared__ PW planes[TR::P * 32];
+  uint64_t pos = start_bit;
+  for (uint64_t b = 0; b < nblocks; b++) {
+    BitReader br;
+    br.init(in, pos);
+    typename TR::Scalar v[N];
+    const uint32_t bits = decode_block<TYPE, DIMS, REV>(v, prm, br, planes);
+    lengths[b] = (uint16_t)bits;
+    pos += bits;
+  }
+}
+
 }  // namespace zb

@@ -410,4 +410,51 @@ decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params 
   scatter4(v, data, g, locate4(g, b));
 }
 
+// coded length of the 4-D block at the reader's position (index rebuild for foreign streams)
+template <int TYPE>
+__device__ uint32_t block_length4(BitReader& br, const Params& prm, uint32_t* pl)
+{
+  using TR = Traits<TYPE>;
+  const bool reversible = prm.minexp < kMinExp;
+  uint32_t bits = 0, maxprec = prm.maxprec;
+  if constexpr (TR::is_fp) {
+    bits = 1;
+    if (!br.get(1))
+      return bits < prm.minbits ? prm.minbits : bits;
+    if (!reversible) {
+      bits += TR::EBITS;
+      const int emax = (int)br.get(TR::EBITS) - TR::EBIAS;
+      maxprec = block_precision<TR>(emax, prm.maxprec, prm.minexp, 4);
+    }
+    else {
+      bits++;
+      if (!br.get(1)) {
+        bits += TR::EBITS;
+        br.skip(TR::EBITS);
+      }
+    }
+  }
+  if (reversible) {
+    maxprec = (uint32_t)br.get(TR::PBITS) + 1;
+    bits += TR::PBITS;
+  }
+  bits += decode_planes4<TR::P>(br, prm.maxbits - bits, maxprec, pl);
+  return bits < prm.minbits ? prm.minbits : bits;
+}
+
+template <int TYPE>
+__global__ void index_scan4_kernel(const void* __restrict__ in, uint64_t start_bit, uint64_t nblocks, Params prm,
+                                   uint16_t* __restrict__ lengths)
+{
+  uint32_t pl[Traits<TYPE>::P * 8];
+  uint64_t pos = start_bit;
+  for (uint64_t b = 0; b < nblocks; b++) {
+    BitReader br;
+    br.init(in, pos);
+    const uint32_t bits = block_length4<TYPE>(br, prm, pl);
+    lengths[b] = (uint16_t)bits;
+    pos += bits;
+  }
+}
+
 }  // namespace zb

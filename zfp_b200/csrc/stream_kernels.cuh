@@ -138,4 +138,31 @@ compact_blocks(const uint64_t* __restrict__ scratch, uint32_t slot_words, const 
   bw.flush();
 }
 
+// Bit-granular device copy: dst[dst_bit, dst_bit+nbits) = src[src_bit, src_bit+nbits).  Words of dst
+// fully inside the range are overwritten; the (at most two) partially covered words are OR-merged,
+// so their target bits must be zero beforehand.  Used to place slab streams produced on different
+// GPUs (or at a different bit phase) into one stream.
+__global__ void __launch_bounds__(256)
+bitcopy_kernel(uint64_t* __restrict__ dst, uint64_t dst_bit, const uint64_t* __restrict__ src, uint64_t src_bit, uint64_t nbits)
+{
+  const uint64_t w0 = dst_bit >> 6, w1 = (dst_bit + nbits + 63) >> 6;  // destination words [w0, w1)
+  for (uint64_t w = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += (uint64_t)gridDim.x * blockDim.x) {
+    // destination bit range covered by this word, clipped to the copy range
+    const uint64_t lo = w * 64 > dst_bit ? w * 64 : dst_bit;
+    const uint64_t hi = (w + 1) * 64 < dst_bit + nbits ? (w + 1) * 64 : dst_bit + nbits;
+    const uint32_t len = (uint32_t)(hi - lo);
+    const uint64_t s = src_bit + (lo - dst_bit);  // first source bit
+    const uint32_t sh = (uint32_t)(s & 63);
+    uint64_t v = src[s >> 6] >> sh;
+    if (sh && sh + len > 64)
+      v |= src[(s >> 6) + 1] << (64 - sh);
+    v &= lowmask64(len);
+    v <<= (uint32_t)(lo & 63);
+    if (len == 64)
+      dst[w] = v;
+    else
+      atomicOr(reinterpret_cast<unsigned long long*>(dst + w), (unsigned long long)v);
+  }
+}
+
 }  // namespace zb

@@ -53,5 +53,7 @@ struct DecodeArgs {
 // one translation unit per scalar type and direction (inst_*.cu) defines these
 template <int TYPE> cudaError_t launch_encode_t(int dims, int out_mode, const EncodeArgs& a);
 template <int TYPE> cudaError_t launch_decode_t(int dims, int offs_mode, const DecodeArgs& a);
+// sequential rebuild of the block-length index of a variable-rate stream
+template <int TYPE> cudaError_t launch_index_t(int dims, const DecodeArgs& a, uint16_t* lengths);
 
 }  // namespace zb

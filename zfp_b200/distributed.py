@@ -1,0 +1,103 @@
+"""Slab-partitioned multi-GPU compression (the reference has no multi-GPU path).
+
+The array is cut into block-aligned slabs along its slowest dimension, one per rank (one process
+per GPU).  Because zfp's stream order is block order with the slowest dimension outermost
+(src/template/compress.c:72-74), a slab is a contiguous range of blocks AND a contiguous range of
+the stream:
+
+* fixed rate: slab g starts at bit  start + blocks_before(g) * maxbits  - no communication;
+* variable rate: every rank encodes its slab, the ranks all_gather ONE integer (their slab's bit
+  length), an exclusive prefix gives each slab's base bit, and the slab stream is placed there with a
+  bit-granular copy (libzfp_b200's zfp_b200_bitcopy on the device).
+
+The per-slab codec is pluggable so that the host logic is testable on CPU (gloo, world_size 2) with
+the oracle standing in for the CUDA backend; the default codec is the CUDA backend.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class SlabPlan:
+    rank: int
+    world: int
+    shape: tuple          # global shape, slowest dimension first
+    z0: int               # first index of this rank's slab along the slowest dimension
+    z1: int               # one past the last
+    blocks_before: int    # blocks of all lower-ranked slabs
+    blocks: int           # blocks in this slab
+
+    @property
+    def slab_shape(self):
+        return (self.z1 - self.z0,) + tuple(self.shape[1:])
+
+
+def plan_slabs(shape, world):
+    """Block-aligned partition of the slowest dimension into `world` contiguous slabs."""
+    shape = tuple(int(v) for v in shape)
+    layers = (shape[0] + 3) // 4
+    per_layer = 1
+    for n in shape[1:]:
+        per_layer *= (n + 3) // 4
+    plans = []
+    for g in range(world):
+        l0, l1 = g * layers // world, (g + 1) * layers // world
+        z0, z1 = min(4 * l0, shape[0]), min(4 * l1, shape[0])
+        plans.append(SlabPlan(g, world, shape, z0, z1, l0 * per_layer, (l1 - l0) * per_layer))
+    return plans
+
+
+def place_bits(dst_words, dst_bit, src_words, nbits):
+    """Host (numpy) version of the bit-granular placement: OR src[0, nbits) into dst at dst_bit."""
+    if nbits == 0:
+        return
+    nwords = (nbits + 63) // 64
+    src = np.ascontiguousarray(src_words[:nwords], dtype=np.uint64).copy()
+    if nbits % 64:
+        src[-1] &= np.uint64((1 << (nbits % 64)) - 1)
+    w0, sh = dst_bit // 64, dst_bit % 64
+    if sh == 0:
+        dst_words[w0:w0 + nwords] |= src
+    else:
+        dst_words[w0:w0 + nwords] |= src << np.uint64(sh)
+        spill = src >> np.uint64(64 - sh)
+        hi = dst_words[w0 + 1:w0 + 1 + nwords]
+        hi |= spill[:len(hi)]
+
+
+class CudaCodec:
+    """Per-slab codec backed by libzfp_b200 (device tensors)."""
+
+    def compress(self, slab, mode):
+        import zfp_b200
+        c = zfp_b200.compress(slab, **mode)
+        lengths = c.stream.index_lengths() if not zfp_b200.api.is_fixed_rate_mode(mode) else None
+        nbits = int(lengths.astype(np.int64).sum()) if lengths is not None else None
+        return c, nbits
+
+    def fixed_bits_per_block(self, dtype_name, dims, mode):
+        import zfp_b200
+        return zfp_b200.api.mode_params(mode, dtype_name, dims)[1]
+
+
+def slab_base_bits(local_bits, start_bit=0, group=None):
+    """all_gather the slab bit lengths and return (base bit of this rank, list of all lengths).
+
+    One small collective (one int64 per rank) - the only communication of the variable-rate path."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.tensor([int(local_bits)], dtype=torch.int64, device=dev)
+    everyone = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(everyone, mine, group=group)
+    lengths = [int(t.item()) for t in everyone]
+    return start_bit + sum(lengths[:rank]), lengths
+
+
+def fixed_rate_base_bit(plan, maxbits, start_bit=0):
+    """Deterministic slab offset for fixed-rate streams - no communication."""
+    return start_bit + plan.blocks_before * maxbits
