@@ -28,9 +28,15 @@ ZFP_MIN_EXP = -1074
 ZFP_MAX_BITS = 16658
 
 
+REF_CUDA_SO = os.path.join(HERE, "_ref", "libzfp_ref_cuda.so")
+
+
 def build(ref=True):
     """(Re)build the oracle libraries with oracle/Makefile."""
-    targets = ["port"] + (["ref"] if ref and os.path.isdir(os.environ.get("ZFP_REFERENCE", "/root/reference")) else [])
+    have_ref = ref and os.path.isdir(os.environ.get("ZFP_REFERENCE", "/root/reference"))
+    targets = ["port"] + (["ref"] if have_ref else [])
+    if have_ref and os.path.exists(os.path.join(HERE, "..", "zfp_b200", "lib", "libzfp_b200.so")):
+        targets.append("ref_cuda")
     subprocess.check_call(["make", "-s", "-C", HERE] + targets)
 
 
@@ -153,10 +159,11 @@ class Reference:
 
     SERIAL, OMP = 0, 1
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO + " (run `make -C oracle ref` where /root/reference exists)")
-        L = C.CDLL(REF_SO)
+    def __init__(self, so=None):
+        so = so or REF_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(so + " (run `make -C oracle ref` where /root/reference exists)")
+        L = C.CDLL(so)
         vp, sz = C.c_void_p, C.c_size_t
         L.stream_open.restype = vp
         L.stream_open.argtypes = [vp, sz]

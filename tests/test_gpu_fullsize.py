@@ -163,3 +163,16 @@ def test_c5_more_than_2p32_values_on_one_gpu(zb, port):
     c = zb.compress(x, **mode)
     assert c.nbytes == 1280 * 2048 * 2048
     check_slabs(zb, port, x, c, mode, [(0, 4), (1100, 1104), (1276, 1280)])
+
+
+def test_reversible_fp64_1024cubed_stream_beyond_2p32_bits(zb, port):
+    """Lossless fp64 at 1024^3: ~3.6 GiB of stream, i.e. bit offsets far beyond 2^32 in the block
+    index scan and the compaction (regression: a 32-bit tile scan once corrupted such streams)."""
+    import torch
+    x = device_field((1024, 1024, 1024), torch.float64)
+    mode = {"reversible": True}
+    c = zb.compress(x, **mode)
+    lengths = c.stream.index_lengths()
+    assert int(lengths.astype(np.int64).sum()) > 2 ** 34
+    y = check_slabs(zb, port, x, c, mode, [(0, 4), (1020, 1024)], lengths)
+    assert torch.equal(x.view(torch.int64), y.view(torch.int64))

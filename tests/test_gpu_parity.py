@@ -197,3 +197,35 @@ def test_openmp_reference_stream_is_identical(zb, ref):
         got, _ = zb.compress_numpy(a, **mode)
         assert got.tobytes() == ref.compress(a, policy=0, **mode).tobytes()
         assert got.tobytes() == ref.compress(a, policy=1, threads=4, **mode).tobytes()
+
+
+def test_reference_library_with_our_backend_as_its_cuda_policy(port):
+    """INTEGRATION.md section A, executed: the unmodified reference libzfp built with -DZFP_WITH_CUDA
+    and linked against libzfp_b200.so instead of src/cuda_zfp.  Its own zfp_compress / zfp_decompress
+    under zfp_exec_cuda now run our kernels (host arrays, as in the reference's CUDA tests,
+    tests/src/endtoend/cudaExecBase.c) and must reproduce the serial streams."""
+    from oracle.oracle import REF_CUDA_SO, Reference
+    if not os.path.exists(REF_CUDA_SO):
+        pytest.skip("oracle/_ref/libzfp_ref_cuda.so not built")
+    R = Reference(REF_CUDA_SO)
+    for dtype, shape in ((np.float64, (33, 36, 40)), (np.float32, (65, 70)), (np.int32, (1000,)), (np.int64, (12, 16, 20))):
+        a = make_field(shape, dtype, seed=31, kind="smooth")
+        for rate in (4, 8, 19):
+            mode = {"rate": rate}
+            serial = R.compress(a, policy=0, **mode)
+            cuda = R.compress(a, policy=2, **mode)
+            assert cuda.tobytes() == serial.tobytes(), (shape, rate)
+            assert cuda.tobytes() == port.compress(a, **mode).tobytes()
+            # decompress through the reference API with the CUDA policy
+            out = np.empty_like(a)
+            n = list(reversed(a.shape)) + [0] * (4 - a.ndim)
+            L = R.L
+            f, dims = R._field(out.ctypes.data, dtype, n, None)
+            words = np.concatenate([cuda, np.zeros(4, dtype=np.uint64)])
+            bs = L.stream_open(words.ctypes.data, words.nbytes)
+            z = L.zfp_stream_open(bs)
+            R._set_mode(z, mode, dtype, dims)
+            assert L.zfp_stream_set_execution(z, 2)
+            assert L.zfp_decompress(z, f) == cuda.nbytes
+            L.zfp_field_free(f); L.zfp_stream_close(z); L.stream_close(bs)
+            assert out.tobytes() == R.decompress(serial, a.shape, a.dtype, **mode).tobytes()

@@ -265,19 +265,25 @@ def max_stream_words(shape, dtype, mode, start_bit=0):
     return n // 8 + (start_bit + 63) // 64 + 1
 
 
-def compress(x, out=None, start_bit=0, header=False, cuda_stream=None, async_fixed_rate=False, **mode):
+def compress(x, out=None, start_bit=0, header=False, cuda_stream=None, async_fixed_rate=False, reuse=None, **mode):
     """Compress a CUDA tensor (any strides) into a device-resident zfp stream.
 
     Mirrors zfp_compress on a zfp_field over a device pointer (include/zfp.h:585-590).
+    `reuse`: a previous `Compressed` of the same shape/dtype/mode whose zfp_stream, bit stream and
+    block index are recycled (what a C caller does by keeping its zfp_stream and rewinding it).
     """
     torch = _torch()
     if not x.is_cuda:
         raise ValueError("compress() wants a CUDA tensor; use compress_numpy() for host arrays")
     L = load_library()
     zt = _tensor_type(x)
-    if out is None:
-        out = torch.empty(max_stream_words(x.shape, x.dtype, mode, start_bit), dtype=torch.int64, device=x.device)
-    s = Stream(out.data_ptr(), out.numel() * 8, mode, zt, x.dim(), cuda_stream, async_fixed_rate)
+    if reuse is not None and reuse.mode == dict(mode) and reuse.dtype == x.dtype and len(reuse.shape) == x.dim():
+        out, s = reuse.words, reuse.stream
+        L.zfp_stream_rewind(s.z)
+    else:
+        if out is None:
+            out = torch.empty(max_stream_words(x.shape, x.dtype, mode, start_bit), dtype=torch.int64, device=x.device)
+        s = Stream(out.data_ptr(), out.numel() * 8, mode, zt, x.dim(), cuda_stream, async_fixed_rate)
     f = _make_field(L, x.data_ptr(), zt, tuple(x.shape), tuple(x.stride()))
     if start_bit:
         L.stream_wseek(s.bs, start_bit)

@@ -42,6 +42,35 @@ __device__ __forceinline__ uint32_t cta_excl_scan(uint32_t v, uint32_t& total)
   return ws[wid] + incl - v;
 }
 
+// 64-bit flavour for the tile-level scan: 1024 tiles of up to 4096 * 16658 bits overflow 32 bits
+__device__ __forceinline__ uint64_t cta_excl_scan64(uint64_t v, uint64_t& total)
+{
+  __shared__ uint64_t ws[33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  uint64_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) ws[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint64_t s = lane < nw ? ws[lane] : 0, si = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t t = __shfl_up_sync(0xffffffffu, si, d);
+      if (lane >= d) si += t;
+    }
+    ws[lane] = si - s;
+    if (lane == 31) ws[32] = si;
+  }
+  __syncthreads();
+  total = ws[32];
+  return ws[wid] + incl - v;
+}
+
 __global__ void __launch_bounds__(kScanThreads)
 scan_tile_sums(const uint16_t* __restrict__ lengths, uint64_t n, uint64_t* __restrict__ tile_sum)
 {
@@ -66,9 +95,8 @@ scan_tile_offsets(uint64_t* __restrict__ tile_sum, uint64_t ntiles, uint64_t* __
   for (uint64_t t0 = 0; t0 < ntiles; t0 += blockDim.x) {
     uint64_t i = t0 + threadIdx.x;
     uint64_t v = i < ntiles ? tile_sum[i] : 0;
-    // tile sums fit 32 bits (4096 * 16658), their running total does not: scan 32-bit, carry 64-bit
-    uint32_t total;
-    uint32_t excl = cta_excl_scan((uint32_t)v, total);
+    uint64_t total;
+    uint64_t excl = cta_excl_scan64(v, total);
     if (i < ntiles)
       tile_sum[i] = carry + excl;
     __syncthreads();
