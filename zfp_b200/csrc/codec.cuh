@@ -536,9 +536,8 @@ __device__ __forceinline__ uint32_t encode_planes_staged(StageWriter& bw, uint32
 {
   const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
   const uint32_t start = bw.tell();
-  uint64_t seen = 0;  // OR of the planes fetched so far
   uint64_t r = 0;     // group-tested bits of the current plane still to code (bit 0 = coefficient pos)
-  uint32_t pos = 0;   // coefficients of the current plane settled so far
+  uint32_t pos = 0;   // coefficients settled so far: carries over as the next plane's verbatim count n
   int k = P;
   for (;;) {
     uint32_t vlo = 0, vhi = 0, l1 = 0, l2 = 0;
@@ -548,14 +547,12 @@ __device__ __forceinline__ uint32_t encode_planes_staged(StageWriter& bw, uint32
       if (--k < kmin || bw.tell() - start >= budget)
         break;
       const uint64_t x = sp[k * 32];
-      const uint32_t n = seen ? 64 - (uint32_t)__clzll((long long)seen) : 0;  // <= N
-      seen |= x;
+      const uint32_t n = pos;  // <= N
       l1 = n < 32 ? n : 32;
       l2 = n - l1;
       vlo = (uint32_t)x & mask32(l1);
       vhi = (uint32_t)(x >> 32) & mask32(l2);
       r = n < 64 ? x >> n : 0;
-      pos = n;
       fresh = true;
     }
     bw.put32(vlo, l1);
@@ -750,22 +747,38 @@ template <> struct FpBits<double> {
 };
 
 // frexp exponent of the largest finite magnitude in the block, clamped as encodef.c:10-27;
-// NaNs never win the comparison (encodef.c:35-37 uses `max < f`)
-template <class TR, int N>
+// NaNs never win the comparison (encodef.c:35-37 uses `max < f`).  EXACT = false (lossy modes,
+// where NaN / infinity inputs are undefined behaviour upstream, docs/source/faq.rst:282-289) takes
+// the maximum over the words holding the exponent only and ORs the rest for the zero test.
+template <class TR, int N, bool EXACT>
 __device__ __forceinline__ int block_emax(const typename TR::Scalar (&v)[N])
 {
   using U = typename TR::UInt;
   const U absmask = ~(U)0 >> 1, infbits = (U)((1u << TR::EBITS) - 1) << TR::MANT;
+  if constexpr (!EXACT && sizeof(U) == 8) {
+    uint32_t top = 0, any_hi = 0, any_lo = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint64_t b = FpBits<typename TR::Scalar>::bits(v[i]);
+      const uint32_t hi = (uint32_t)(b >> 32) & 0x7fffffffu;
+      top = hi > top ? hi : top;
+      any_hi |= hi;
+      any_lo |= (uint32_t)b;
+    }
+    const int E = (int)(top >> 20);
+    if (E) return E - TR::EBIAS + 1;
+    return (any_hi | any_lo) ? 1 - TR::EBIAS : -TR::EBIAS;
+  }
   U m = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) {
     U a = FpBits<typename TR::Scalar>::bits(v[i]) & absmask;
-    a = a > infbits ? 0 : a;
+    if (EXACT) a = a > infbits ? 0 : a;
     m = a > m ? a : m;
   }
   int E = (int)(m >> TR::MANT);
   // inf: frexp leaves the exponent 0 in glibc; the value is irrelevant but keep it
-  if (m == infbits) return 0 > 1 - TR::EBIAS ? 0 : 1 - TR::EBIAS;
+  if (EXACT && m == infbits) return 0 > 1 - TR::EBIAS ? 0 : 1 - TR::EBIAS;
   if (E) return E - TR::EBIAS + 1;
   return m ? 1 - TR::EBIAS : -TR::EBIAS;
 }
@@ -859,7 +872,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   Int q[N];
 
   if constexpr (TR::is_fp) {
-    const int emax = block_emax<TR>(v);
+    const int emax = block_emax<TR, N, REV>(v);
     if (!reversible) {
       maxprec = block_precision<TR>(emax, prm.maxprec, prm.minexp, DIMS);
       const uint32_t e = maxprec ? (uint32_t)(emax + TR::EBIAS) : 0;

@@ -29,11 +29,22 @@ __device__ __forceinline__ BlockPos<DIMS> locate(const Geom& g, uint64_t b)
   BlockPos<DIMS> p;
   p.offset = 0;
   p.full = true;
+  const bool small = (g.nblocks >> 32) == 0;  // 32-bit division is several times cheaper
 #pragma unroll
   for (int d = 0; d < 3; d++) {
     if (d < DIMS) {
-      uint64_t q = d + 1 < DIMS ? b / g.nb[d] : 0;
-      uint64_t c = d + 1 < DIMS ? b - q * g.nb[d] : b;
+      uint64_t q = 0, c = b;
+      if (d + 1 < DIMS) {
+        if (small) {
+          const uint32_t q32 = (uint32_t)b / (uint32_t)g.nb[d];
+          c = (uint32_t)b - q32 * (uint32_t)g.nb[d];
+          q = q32;
+        }
+        else {
+          q = b / g.nb[d];
+          c = b - q * g.nb[d];
+        }
+      }
       b = q;
       uint64_t org = 4 * c, left = g.n[d] - org;
       p.ext[d] = left < 4 ? (uint32_t)left : 4u;
