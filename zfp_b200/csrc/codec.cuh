@@ -268,15 +268,16 @@ struct StageReader {
     lo = __funnelshift_rc(lo, hi, len);
     hi = __funnelshift_rc(hi, 0, len);
     avail -= len;
-    if (avail <= 32) {
-      const uint32_t w = *p;
-      p += 32;
-      // append w at bit position avail (0..32)
-      lo |= avail < 32 ? w << avail : 0;
-      hi = __funnelshift_l(w, 0, avail) | (avail == 32 ? w : 0);
-      // for avail == 32 the word lands exactly in hi; funnelshift_l masks the shift to 0 there
-      avail += 32;
-    }
+    // branch-free refill: the next word is always fetched (a lane-private shared-memory load) and
+    // merged at bit position `avail` only when the window has dropped to 32 valid bits or fewer
+    const uint32_t w = *p;
+    const bool need = avail <= 32;
+    const uint32_t add_lo = __funnelshift_lc(0, w, avail);  // w << avail, 0 when avail == 32
+    const uint32_t add_hi = __funnelshift_lc(w, 0, avail);  // w >> (32 - avail), w when avail == 32
+    lo |= need ? add_lo : 0u;
+    hi |= need ? add_hi : 0u;
+    avail += need ? 32u : 0u;
+    p += need ? 32 : 0;
   }
   __device__ __forceinline__ uint32_t get32(uint32_t len)  // len <= 32
   {
@@ -649,13 +650,15 @@ __device__ __forceinline__ uint32_t decode_planes_staged(StageReader& br, uint32
   bool open = false;  // a plane is in progress (its next item starts with a group test)
   int k = P, lowest = P;
   for (;;) {
-    if (!open) {
-      if (!bits || --k < kmin)
-        break;
-      const uint32_t m = n < bits ? n : bits;
+    const bool start = !open;
+    if (start && (!bits || --k < kmin))
+      break;
+    {
+      // verbatim bits of a plane that starts now (zero-length reads otherwise: uniform code)
+      const uint32_t m = start ? (n < bits ? n : bits) : 0u;
       const uint32_t l1 = m < 32 ? m : 32, l2 = m - l1;
-      x = br.get32(l1);
-      x |= (uint64_t)br.get32(l2) << 32;
+      const uint32_t v1 = br.get32(l1), v2 = br.get32(l2);
+      x = start ? ((uint64_t)v1 | ((uint64_t)v2 << 32)) : x;
       bits -= m;
       open = true;
     }

@@ -246,7 +246,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 // Fixed rate, word-aligned blocks, fast path: each lane first copies its block's words to a
 // shared-memory column (all loads in flight at once instead of one dependent global load per
 // word inside the serial decoder), then decodes from there (StageReader).
-constexpr int kReadSlack = 2;  // the reader's window may prefetch up to two words past the block
+constexpr int kReadSlack = 3;  // the window prefetches up to two words past the block and always peeks one more
 
 template <int TYPE, int DIMS, bool REV>
 __global__ void __launch_bounds__(kThreads)
@@ -275,6 +275,7 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   }
   stage[words * 32] = 0;
   stage[(words + 1) * 32] = 0;
+  stage[(words + 2) * 32] = 0;
 
   StageReader br;
   br.init(stage);
