@@ -104,7 +104,7 @@ def load_library(build_if_missing=True):
     """Load libzfp_b200.so (building it with nvcc if absent).  Raises if it cannot be had."""
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("ZFP_B200_LIB", _build.LIB)  # developer override for A/B experiments
         if not os.path.exists(path):
             if not build_if_missing:
                 raise FileNotFoundError(path)

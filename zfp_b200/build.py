@@ -11,9 +11,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ_DIR = os.path.join(HERE, "build")
+OBJ_DIR = os.path.join(HERE, "build", "default")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libzfp_b200.so")
+# developer knobs for A/B experiments: an alternative library name and extra nvcc flags (-D...)
+LIB = os.path.join(LIB_DIR, os.environ.get("ZFP_B200_LIB_NAME", "libzfp_b200.so"))
+EXTRA = os.environ.get("ZFP_B200_EXTRA_FLAGS", "").split()
+if EXTRA:
+    OBJ_DIR = os.path.join(HERE, "build", "variant_" + os.environ.get("ZFP_B200_LIB_NAME", "x"))
 INCLUDE = os.path.join(HERE, "..", "include")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17"] + ARCH + ["-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
@@ -37,7 +41,7 @@ def _nvcc():
 
 
 def _compile(src, obj, verbose):
-    cmd = _nvcc() + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    cmd = _nvcc() + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, r.returncode, r.stderr, " ".join(cmd)
 

@@ -477,6 +477,53 @@ __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWo
   }
 }
 
+// Two-phase variants for the staged fast path: only 32 planes (bits 32H .. 32H+31 of every
+// coefficient) are resident in shared memory at a time, as sp[(k - 32H) * 32].  Halves the plane
+// storage (more resident warps) and skips the low half entirely when no block of the warp needs it.
+template <int H, class UInt, int N>
+__device__ __forceinline__ void to_planes_half(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
+{
+  constexpr int G = (N + 31) / 32;
+  uint32_t a[G][32];
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      a[g][i] = (32 * g + i < N) ? (uint32_t)(u[(32 * g + i) % N] >> (32 * H)) : 0u;
+    transpose32(a[g]);
+  }
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    if (G == 2)
+      sp[k * 32] = (typename PlaneWord<N>::type)((uint64_t)a[0][k] | ((uint64_t)a[G - 1][k] << 32));
+    else
+      sp[k * 32] = (typename PlaneWord<N>::type)a[0][k];
+  }
+}
+
+// OR planes 32H .. 32H+31 (those with absolute index >= kstop; the rest read as zero) into u
+template <int H, class UInt, int N>
+__device__ __forceinline__ void from_planes_half(UInt (&u)[N], const typename PlaneWord<N>::type* sp, int kstop)
+{
+  constexpr int G = (N + 31) / 32;
+  uint32_t a[G][32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    typename PlaneWord<N>::type x = (32 * H + k >= kstop) ? sp[k * 32] : 0;
+    a[0][k] = (uint32_t)x;
+    if (G == 2)
+      a[G - 1][k] = (uint32_t)((uint64_t)x >> 32);
+  }
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    transpose32(a[g]);
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if (32 * g + i < N)
+        u[(32 * g + i) % N] |= (UInt)((UInt)a[g][i] << (32 * H));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // embedded coder on plane words (N <= 64)
 // ------------------------------------------------------------------------------------------------
@@ -531,23 +578,36 @@ __device__ __forceinline__ uint32_t encode_planes(Writer& bw, uint32_t budget, u
 // implied), with the closing '0' folded in when it was the plane's last run.  Lanes whose planes
 // have several runs simply spend more iterations.  The bit budget is enforced by truncation in
 // StageWriter::finish().
-template <int N, int P>
-__device__ __forceinline__ uint32_t encode_planes_staged(StageWriter& bw, uint32_t budget, uint32_t maxprec,
-                                                         const typename PlaneWord<N>::type* sp)
+struct EncodeState {
+  uint64_t r;     // group-tested bits of the current plane still to code (bit 0 = coefficient pos)
+  uint32_t pos;   // coefficients settled so far: carries over as the next plane's verbatim count n
+  int k;          // current plane (starts at P)
+  bool done;      // budget exhausted or all planes coded
+};
+
+// Codes planes down to klo (inclusive) from the resident half whose first plane is kbase; returns
+// with st.done set when the block is finished, or cleared when it needs planes below klo.
+template <int N>
+__device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t start, uint32_t budget, int kmin, int klo,
+                                                     int kbase, EncodeState& st, const typename PlaneWord<N>::type* sp)
 {
-  const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
-  const uint32_t start = bw.tell();
-  uint64_t r = 0;     // group-tested bits of the current plane still to code (bit 0 = coefficient pos)
-  uint32_t pos = 0;   // coefficients settled so far: carries over as the next plane's verbatim count n
-  int k = P;
+  uint64_t r = st.r;
+  uint32_t pos = st.pos;
+  int k = st.k;
+  bool done = false;
   for (;;) {
     uint32_t vlo = 0, vhi = 0, l1 = 0, l2 = 0;
     bool fresh = false;
     if (!r) {
       // previous plane complete: fetch the next one
-      if (--k < kmin || bw.tell() - start >= budget)
+      if (k - 1 < kmin || bw.tell() - start >= budget) {
+        done = true;
         break;
-      const uint64_t x = sp[k * 32];
+      }
+      if (k - 1 < klo)
+        break;
+      k--;
+      const uint64_t x = sp[(k - kbase) * 32];
       const uint32_t n = pos;  // <= N
       l1 = n < 32 ? n : 32;
       l2 = n - l1;
@@ -576,8 +636,10 @@ __device__ __forceinline__ uint32_t encode_planes_staged(StageWriter& bw, uint32
     else if (fresh)
       bw.put32(0, pos < N ? 1u : 0u);  // no new coefficient in this plane: just the '0' test
   }
-  const uint32_t used = bw.tell() - start;
-  return used < budget ? used : budget;
+  st.r = r;
+  st.pos = pos;
+  st.k = k;
+  st.done = done;
 }
 
 // Mirror image.  Decoded planes are stored to sp[k*32]; returns bits consumed and, through
@@ -640,19 +702,35 @@ __device__ __forceinline__ void decode_group_exact(Reader& br, uint32_t& bits, u
 // group-tested item).  Budget accounting is exact at every step, including the reference's
 // deposit-on-exhaustion rule (decode.c:103-111): a run is limited to min(bits left, N-1-n) zeros
 // and the one-bit is deposited where the scan stopped.
-template <int N, int P>
-__device__ __forceinline__ uint32_t decode_planes_staged(StageReader& br, uint32_t budget, uint32_t maxprec,
-                                                         typename PlaneWord<N>::type* sp, int& kstop)
+struct DecodeState {
+  uint64_t x;     // plane being assembled
+  uint32_t bits;  // budget left
+  uint32_t n;     // coefficients significant so far
+  int k;          // current plane (starts at P)
+  int lowest;     // lowest plane stored so far (P when none)
+  bool open;      // a plane is in progress (its next item starts with a group test)
+  bool done;      // budget exhausted or all planes decoded
+};
+
+template <int N>
+__device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, int klo, int kbase, DecodeState& st,
+                                                     typename PlaneWord<N>::type* sp)
 {
-  const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
-  uint32_t bits = budget, n = 0;
-  uint64_t x = 0;
-  bool open = false;  // a plane is in progress (its next item starts with a group test)
-  int k = P, lowest = P;
+  uint32_t bits = st.bits, n = st.n;
+  uint64_t x = st.x;
+  bool open = st.open, finished = false;
+  int k = st.k, lowest = st.lowest;
   for (;;) {
     const bool start = !open;
-    if (start && (!bits || --k < kmin))
-      break;
+    if (start) {
+      if (!bits || k - 1 < kmin) {
+        finished = true;
+        break;
+      }
+      if (k - 1 < klo)
+        break;
+      k--;
+    }
     {
       // verbatim bits of a plane that starts now (zero-length reads otherwise: uniform code)
       const uint32_t m = start ? (n < bits ? n : bits) : 0u;
@@ -725,13 +803,18 @@ __device__ __forceinline__ uint32_t decode_planes_staged(StageReader& br, uint32
       }
     }
     if (done) {
-      sp[k * 32] = (typename PlaneWord<N>::type)x;
+      sp[(k - kbase) * 32] = (typename PlaneWord<N>::type)x;
       lowest = k;
       open = false;
     }
   }
-  kstop = lowest;
-  return budget - bits;
+  st.bits = bits;
+  st.n = n;
+  st.x = x;
+  st.open = open;
+  st.k = k;
+  st.lowest = lowest;
+  st.done = finished;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -872,6 +955,9 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   constexpr int N = 1 << (2 * DIMS), P = TR::P;
   constexpr bool reversible = REV;  // prm.minexp < ZFP_MIN_EXP, resolved by the launcher
   uint32_t bits = 0, maxprec = prm.maxprec;
+  // A block that codes as a single '0' bit skips the coefficient stage by flag, not by an early
+  // return: in the staged path all 32 lanes of the warp must reach the two-phase vote below.
+  bool coded = true, pad = true;
   Int q[N];
 
   if constexpr (TR::is_fp) {
@@ -879,14 +965,9 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     if (!reversible) {
       maxprec = block_precision<TR>(emax, prm.maxprec, prm.minexp, DIMS);
       const uint32_t e = maxprec ? (uint32_t)(emax + TR::EBIAS) : 0;
-      if (!e) {
-        bw.put(0, 1);
-        bits = 1;
-        if (bits < prm.minbits) { bw.pad(prm.minbits - bits); bits = prm.minbits; }
-        return bits;
-      }
-      bits = 1 + TR::EBITS;
-      bw.put(2 * (uint64_t)e + 1, bits);
+      coded = e != 0;
+      bits = coded ? 1 + TR::EBITS : 1;
+      bw.put(coded ? 2 * (uint64_t)e + 1 : 0, bits);
       cast_fwd<TR>(q, v, emax);
     }
     else {
@@ -911,11 +992,14 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
         const uint32_t e = (uint32_t)(emax + TR::EBIAS);
         if (!e) {
           bw.put(0, 1);
-          return 1;  // no minbits padding on this path (revencodef.c:64-69)
+          bits = 1;
+          coded = pad = false;  // no minbits padding on this path (revencodef.c:64-69)
         }
-        bw.put(1, 2);
-        bw.put(e, TR::EBITS);
-        bits = 2 + TR::EBITS;
+        else {
+          bw.put(1, 2);
+          bw.put(e, TR::EBITS);
+          bits = 2 + TR::EBITS;
+        }
       }
       else {
         // sign-magnitude bit patterns -> two's complement (revencodef.c:29-41)
@@ -954,16 +1038,41 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     uint32_t prec = any ? (uint32_t)P - (P == 64 ? ctz64((uint64_t)any) : (uint32_t)__ffs((int)any) - 1) : 0;
     prec = prec < prm.maxprec ? prec : prm.maxprec;
     prec = prec > 1 ? prec : 1;
-    bw.put(prec - 1, TR::PBITS);
-    bits += TR::PBITS;
+    if (coded) {
+      bw.put(prec - 1, TR::PBITS);
+      bits += TR::PBITS;
+    }
     maxprec = prec;
   }
-  to_planes<UInt, N>(u, sp);
-  if constexpr (Writer::kStaged)
-    bits += encode_planes_staged<N, P>(bw, prm.maxbits - bits, maxprec, sp);
-  else
+  if constexpr (Writer::kStaged) {
+    // two-phase: the high 32 planes first; the low 32 only if some block of the warp still has
+    // budget when it gets there (all 32 lanes reach the vote: the staged kernel has no early exit)
+    const uint32_t budget = prm.maxbits - bits, start = bw.tell();
+    const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+    EncodeState st = { 0, 0, P, !coded };
+    if constexpr (P == 64) {
+      to_planes_half<1, UInt, N>(u, sp);
+      if (!st.done)
+        encode_planes_staged<N>(bw, start, budget, kmin, 32, 32, st, sp);
+      if (__any_sync(0xffffffffu, !st.done)) {
+        to_planes_half<0, UInt, N>(u, sp);
+        if (!st.done)
+          encode_planes_staged<N>(bw, start, budget, kmin, 0, 0, st, sp);
+      }
+    }
+    else {
+      to_planes_half<0, UInt, N>(u, sp);
+      if (!st.done)
+        encode_planes_staged<N>(bw, start, budget, kmin, 0, 0, st, sp);
+    }
+    const uint32_t used = bw.tell() - start;
+    bits += used < budget ? used : budget;
+  }
+  else if (coded) {
+    to_planes<UInt, N>(u, sp);
     bits += encode_planes<N, P>(bw, prm.maxbits - bits, maxprec, sp);
-  if (bits < prm.minbits) {
+  }
+  if (pad && bits < prm.minbits) {
     bw.pad(prm.minbits - bits);
     bits = prm.minbits;
   }
@@ -984,44 +1093,72 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   uint32_t bits = 0, maxprec = prm.maxprec;
   int emax = 0;
   bool reinterpret = false;
+  bool zero = false;  // an all-zero block (single '0' bit) flows through by flag: see encode_block
 
   if constexpr (TR::is_fp) {
     bits = 1;
-    if (!br.get(1)) {
-#pragma unroll
-      for (int i = 0; i < N; i++)
-        v[i] = (Scalar)0;
-      return bits < prm.minbits ? prm.minbits : bits;  // the caller positions the next block
-    }
-    if (!reversible) {
-      bits += TR::EBITS;
-      emax = (int)br.get(TR::EBITS) - TR::EBIAS;
-      maxprec = block_precision<TR>(emax, prm.maxprec, prm.minexp, DIMS);
-    }
-    else {
-      bits++;
-      reinterpret = br.get(1) != 0;
-      if (!reinterpret) {
+    zero = !br.get(1);
+    if (!zero) {
+      if (!reversible) {
         bits += TR::EBITS;
         emax = (int)br.get(TR::EBITS) - TR::EBIAS;
+        maxprec = block_precision<TR>(emax, prm.maxprec, prm.minexp, DIMS);
+      }
+      else {
+        bits++;
+        reinterpret = br.get(1) != 0;
+        if (!reinterpret) {
+          bits += TR::EBITS;
+          emax = (int)br.get(TR::EBITS) - TR::EBIAS;
+        }
       }
     }
   }
-  if (reversible) {
+  if (reversible && !zero) {
     maxprec = (uint32_t)br.get(TR::PBITS) + 1;
     bits += TR::PBITS;
   }
 
-  int kstop;
-  if constexpr (Reader::kStaged)
-    bits += decode_planes_staged<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
-  else
+  UInt u[N];
+  if constexpr (Reader::kStaged) {
+    const uint32_t budget = prm.maxbits - bits;
+    const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+    DecodeState st = { 0, budget, 0, P, P, false, zero };
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      u[i] = 0;
+    if constexpr (P == 64) {
+      if (!st.done)
+        decode_planes_staged<N>(br, kmin, 32, 32, st, sp);
+      from_planes_half<1, UInt, N>(u, sp, st.lowest);
+      if (__any_sync(0xffffffffu, !st.done)) {
+        if (!st.done)
+          decode_planes_staged<N>(br, kmin, 0, 0, st, sp);
+        from_planes_half<0, UInt, N>(u, sp, st.lowest);
+      }
+    }
+    else {
+      if (!st.done)
+        decode_planes_staged<N>(br, kmin, 0, 0, st, sp);
+      from_planes_half<0, UInt, N>(u, sp, st.lowest);
+    }
+    bits += budget - st.bits;
+  }
+  else if (!zero) {
+    int kstop;
     bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
+    from_planes<UInt, N>(u, sp, kstop);
+  }
+  else {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      u[i] = 0;
+  }
+  if (zero)
+    bits = 1;
   if (bits < prm.minbits)
     bits = prm.minbits;
 
-  UInt u[N];
-  from_planes<UInt, N>(u, sp, kstop);
   Int q[N];
 #pragma unroll
   for (int i = 0; i < N; i++)

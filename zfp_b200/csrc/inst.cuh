@@ -30,7 +30,7 @@ cudaError_t run_encode_staged(const EncodeArgs& a)
 {
   constexpr int N = 1 << (2 * DIMS);
   auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
-  const size_t smem = (size_t)(kThreads / 32) * (Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type) +
+  const size_t smem = (size_t)(kThreads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4);
   static size_t allowed = 0;  // per kernel instance
   if (smem > 48 * 1024 && smem > allowed) {
@@ -65,7 +65,7 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
 {
   constexpr int N = 1 << (2 * DIMS);
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
-  const size_t smem = (size_t)(kThreads / 32) * (Traits<TYPE>::P * 32 * sizeof(typename PlaneWord<N>::type) +
+  const size_t smem = (size_t)(kThreads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4);
   static size_t allowed = 0;
   if (smem > 48 * 1024 && smem > allowed) {

@@ -209,10 +209,14 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 // Fixed rate with word-aligned blocks, fast path: bits are staged per lane in shared memory
 // (StageWriter) and leave with 64-bit stores.  Dynamic shared memory per warp:
 // planes (P*32 plane words) followed by (maxbits/32 + kStageSlack) * 32 staging words.
-constexpr int kStageSlack = 8;  // words of overshoot room: one plane may exceed the budget by < 200 bits
+#ifndef ZB_MINBLOCKS64
+#define ZB_MINBLOCKS64 5  // launch-bounds hint for the 64-bit staged kernels; 5 measured best of {4,5,6,8} on B200
+#endif
+constexpr int kStageSlack = 8;    // words of overshoot room: one plane may exceed the budget by < 200 bits
+constexpr int kStagedPlanes = 32;  // planes resident per phase in the staged kernels (two-phase for 64-bit types)
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? 9 : ZB_MINBLOCKS64)
 encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      uint64_t* __restrict__ out, uint64_t start_bit)
 {
@@ -221,14 +225,16 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
   const uint32_t words = prm.maxbits >> 5;  // 32-bit words per block (even: maxbits % 64 == 0)
-  const uint32_t warp_bytes = TR::P * 32 * (uint32_t)sizeof(PW) + (words + kStageSlack) * 32 * 4;
+  const uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (words + kStageSlack) * 32 * 4;
   char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(base + TR::P * 32 * sizeof(PW)) + (threadIdx.x & 31);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
 
-  const uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (b >= g.nblocks)
-    return;
+  // no early exit: lanes past the end redo the last block and discard it, so that warp-wide votes
+  // inside encode_block always see 32 lanes
+  const uint64_t b_raw = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = b_raw < g.nblocks;
+  const uint64_t b = valid ? b_raw : g.nblocks - 1;
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
   typename TR::Scalar v[N];
   gather<DIMS>(v, data, g, pos);
@@ -238,9 +244,11 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   encode_block<TYPE, DIMS, REV>(v, prm, bw, sp);
   bw.finish(words);
 
-  uint64_t* dst = out + (start_bit >> 6) + b * (uint64_t)(words >> 1);
-  for (uint32_t w = 0; w < words; w += 2)
-    dst[w >> 1] = (uint64_t)stage[w * 32] | ((uint64_t)stage[(w + 1) * 32] << 32);
+  if (valid) {
+    uint64_t* dst = out + (start_bit >> 6) + b * (uint64_t)(words >> 1);
+    for (uint32_t w = 0; w < words; w += 2)
+      dst[w >> 1] = (uint64_t)stage[w * 32] | ((uint64_t)stage[(w + 1) * 32] << 32);
+  }
 }
 
 // Fixed rate, word-aligned blocks, fast path: each lane first copies its block's words to a
@@ -249,7 +257,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 constexpr int kReadSlack = 3;  // the window prefetches up to two words past the block and always peeks one more
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? 9 : ZB_MINBLOCKS64)
 decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      const uint64_t* __restrict__ in, uint64_t start_bit)
 {
@@ -258,14 +266,14 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
   const uint32_t words = prm.maxbits >> 5;
-  const uint32_t warp_bytes = TR::P * 32 * (uint32_t)sizeof(PW) + (words + kReadSlack) * 32 * 4;
+  const uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (words + kReadSlack) * 32 * 4;
   char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(base + TR::P * 32 * sizeof(PW)) + (threadIdx.x & 31);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
 
-  const uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (b >= g.nblocks)
-    return;
+  const uint64_t b_raw = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = b_raw < g.nblocks;  // no early exit (warp-wide votes in decode_block)
+  const uint64_t b = valid ? b_raw : g.nblocks - 1;
   const uint64_t* src = in + (start_bit >> 6) + b * (uint64_t)(words >> 1);
 #pragma unroll 4
   for (uint32_t w = 0; w < words; w += 2) {
@@ -281,8 +289,10 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   br.init(stage);
   typename TR::Scalar v[N];
   decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
-  const BlockPos<DIMS> pos = locate<DIMS>(g, b);
-  scatter<DIMS>(v, data, g, pos);
+  if (valid) {
+    const BlockPos<DIMS> pos = locate<DIMS>(g, b);
+    scatter<DIMS>(v, data, g, pos);
+  }
 }
 
 // OFFS: 0 fixed rate (offset = start + b*maxbits), 1 per-block offsets from the index scan
