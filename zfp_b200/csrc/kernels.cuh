@@ -246,8 +246,18 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 
   if (valid) {
     uint64_t* dst = out + (start_bit >> 6) + b * (uint64_t)(words >> 1);
-    for (uint32_t w = 0; w < words; w += 2)
-      dst[w >> 1] = (uint64_t)stage[w * 32] | ((uint64_t)stage[(w + 1) * 32] << 32);
+    if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      // 16-byte stores: a block's words are contiguous in the stream
+      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll 4
+      for (uint32_t w = 0; w < words; w += 4)
+        dst4[w >> 2] = make_uint4(stage[w * 32], stage[(w + 1) * 32], stage[(w + 2) * 32], stage[(w + 3) * 32]);
+    }
+    else {
+#pragma unroll 4
+      for (uint32_t w = 0; w < words; w += 2)
+        dst[w >> 1] = (uint64_t)stage[w * 32] | ((uint64_t)stage[(w + 1) * 32] << 32);
+    }
   }
 }
 
@@ -275,11 +285,24 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   const bool valid = b_raw < g.nblocks;  // no early exit (warp-wide votes in decode_block)
   const uint64_t b = valid ? b_raw : g.nblocks - 1;
   const uint64_t* src = in + (start_bit >> 6) + b * (uint64_t)(words >> 1);
+  if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll 4
-  for (uint32_t w = 0; w < words; w += 2) {
-    const uint64_t v = __ldg(src + (w >> 1));
-    stage[w * 32] = (uint32_t)v;
-    stage[(w + 1) * 32] = (uint32_t)(v >> 32);
+    for (uint32_t w = 0; w < words; w += 4) {
+      const uint4 v = __ldg(src4 + (w >> 2));
+      stage[w * 32] = v.x;
+      stage[(w + 1) * 32] = v.y;
+      stage[(w + 2) * 32] = v.z;
+      stage[(w + 3) * 32] = v.w;
+    }
+  }
+  else {
+#pragma unroll 4
+    for (uint32_t w = 0; w < words; w += 2) {
+      const uint64_t v = __ldg(src + (w >> 1));
+      stage[w * 32] = (uint32_t)v;
+      stage[(w + 1) * 32] = (uint32_t)(v >> 32);
+    }
   }
   stage[words * 32] = 0;
   stage[(words + 1) * 32] = 0;
