@@ -223,10 +223,10 @@ static int encode_any(int out_mode, int type, uint32_t dims, const void* data, c
 }
 
 static int decode_any(int offs_mode, int type, uint32_t dims, void* data, const Geom& g, const Params& prm, const void* in,
-                      uint64_t start_bit, const uint64_t* offsets, cudaStream_t st)
+                      uint64_t start_bit, const uint64_t* offsets, const uint16_t* lengths, cudaStream_t st)
 {
   static const int staged = getenv("ZFP_B200_NO_STAGED") ? 0 : 1;
-  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, st, staged };
+  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, lengths, st, staged };
   cudaError_t e;
   switch (type) {
     case T_INT32: e = launch_decode_t<T_INT32>((int)dims, offs_mode, a); break;
@@ -291,7 +291,7 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
   }
 
   // variable rate: encode into per-block scratch slots, scan the lengths, compact bit-granularly
-  const uint32_t slot_words = (block_capacity_bits(d) + 63) / 64;
+  const uint32_t slot_words = (block_capacity_bits(d) + 63) / 64 + 4;  // + room for a plane of overshoot past the budget
   const uint64_t slot_bytes = (uint64_t)slot_words * 8;
   uint64_t chunk = ((uint64_t)1 << 30) / slot_bytes;
   chunk = chunk / kScanTile * kScanTile;
@@ -346,7 +346,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   int rc;
 
   if (d->minbits == d->maxbits) {
-    rc = decode_any(0, d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, st);
+    rc = decode_any(0, d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, nullptr, st);
     if (rc) return rc;
     if (end_bit) *end_bit = start_bit + g.nblocks * (uint64_t)d->maxbits;
     return ZFP_B200_OK;
@@ -363,7 +363,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
     // foreign stream: rebuild the index by parsing the stream sequentially on the device
     uint16_t* rebuilt = static_cast<uint16_t*>(scratch(SCR_LENGTHS, g.nblocks * sizeof(uint16_t)));
     if (!rebuilt) return ZFP_B200_ECUDA;
-    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, st, 0 };
+    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, nullptr, st, 0 };
     cudaError_t e;
     switch (d->type) {
       case T_INT32: e = launch_index_t<T_INT32>((int)d->dims, a, rebuilt); break;
@@ -383,7 +383,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   LAUNCHED();
   rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st);
   if (rc) return rc;
-  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, st);
+  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st);
   if (rc) return rc;
   uint64_t h_cursor[2];
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));

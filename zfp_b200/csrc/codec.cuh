@@ -140,17 +140,42 @@ __device__ __forceinline__ uint32_t mask32(uint32_t len)  // low `len` bits set,
   return r;
 }
 
+constexpr uint32_t kPlaneMaxWords = 8;  // a plane appends < 200 bits: 7 words, plus one being filled
+
 struct StageWriter {
   static constexpr bool kStaged = true;
   uint32_t* p;   // next staging word of this lane (stride 32 words)
   uint32_t* p0;
   uint32_t lo, hi, fill;
+  // variable-rate use: the column holds `cap` words; when it runs low the complete words are
+  // drained to the block's slot in global memory (gdst) and `base` counts the drained bits
+  uint32_t* gdst;
+  uint32_t base, cap;
 
-  __device__ __forceinline__ void init(uint32_t* column)
+  __device__ __forceinline__ void init(uint32_t* column, uint32_t* slot = nullptr, uint32_t capacity_words = 0)
   {
     p = p0 = column;
     lo = hi = 0;
     fill = 0;
+    gdst = slot;
+    base = 0;
+    cap = capacity_words;
+  }
+  // variable rate only; call where at most kPlaneMaxWords more words may be appended before the
+  // next call (plane boundaries)
+  __device__ __forceinline__ void drain_if_low()
+  {
+    if (gdst && (uint32_t)(p - p0) > (cap - kPlaneMaxWords) * 32)
+      drain();
+  }
+  __device__ __forceinline__ void drain()
+  {
+    const uint32_t n = (uint32_t)(p - p0) >> 5;
+    for (uint32_t j = 0; j < n; j++)
+      gdst[j] = p0[j * 32];
+    gdst += n;
+    base += n * 32;
+    p = p0;
   }
   __device__ __forceinline__ void put32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
   {
@@ -181,10 +206,21 @@ struct StageWriter {
       p += 32;
       lo = 0;
       fill -= 32;
+      if (gdst && (uint32_t)(p - p0) >= cap * 32)
+        drain();
     }
   }
   __device__ __forceinline__ void pad(uint32_t zeros) { skip(zeros); }
-  __device__ __forceinline__ uint32_t tell() const { return (uint32_t)(p - p0) + fill; }  // (p-p0)/32 words * 32 bits
+  __device__ __forceinline__ uint32_t tell() const { return base + (uint32_t)(p - p0) + fill; }  // (p-p0)/32 words * 32 bits
+  // variable rate: flush everything to the slot
+  __device__ __forceinline__ void finish_slot()
+  {
+    if (fill) {
+      *p = lo;
+      p += 32;
+    }
+    drain();
+  }
   // close the block at exactly total_words 32-bit words: flush, zero-fill, ignore overshoot
   __device__ __forceinline__ void finish(uint32_t total_words)
   {
@@ -254,6 +290,11 @@ struct StageReader {
   const uint32_t* p;  // next word to fetch (stride 32 words)
   uint32_t lo, hi;    // window, LSB first
   uint32_t avail;     // valid bits in the window, 33..64 between calls
+  // variable-rate use: the column holds a `cap`-word window of the block's words, which start at
+  // gsrc (32-bit words) and number `left` from there; restage_if_low() slides the window
+  uint32_t* col;
+  const uint32_t* gsrc;
+  uint32_t left, cap;
 
   __device__ __forceinline__ void init(const uint32_t* column)
   {
@@ -261,6 +302,39 @@ struct StageReader {
     hi = column[32];
     p = column + 64;
     avail = 64;
+    gsrc = nullptr;
+  }
+  // variable rate: (re)fill the column from global memory and position the window `phase` bits in
+  __device__ __forceinline__ void stage(uint32_t phase)
+  {
+    const uint32_t n = left < cap ? left : cap;
+    for (uint32_t j = 0; j < cap; j++)
+      col[j * 32] = j < n ? __ldg(gsrc + j) : 0u;
+    lo = col[0];
+    hi = col[32];
+    p = col + 64;
+    avail = 64;
+    skip32(phase);
+  }
+  __device__ __forceinline__ void init_var(uint32_t* column, uint32_t capacity_words, const uint32_t* src, uint32_t words,
+                                           uint32_t phase)
+  {
+    col = column;
+    cap = capacity_words;
+    gsrc = src;
+    left = words;
+    stage(phase);
+  }
+  // call at plane boundaries: a plane reads < 200 bits, the window looks two words ahead and the
+  // branch-free refill peeks one more
+  __device__ __forceinline__ void restage_if_low()
+  {
+    if (gsrc && (uint32_t)(p - col) > (cap - kPlaneMaxWords - 3) * 32) {
+      const uint32_t consumed = (uint32_t)(p - col) - avail;  // bits, relative to the column start
+      gsrc += consumed >> 5;
+      left = left > (consumed >> 5) ? left - (consumed >> 5) : 0;
+      stage(consumed & 31);
+    }
   }
   __device__ __forceinline__ uint32_t peek32() const { return lo; }
   __device__ __forceinline__ void skip32(uint32_t len)  // len <= 32
@@ -587,7 +661,9 @@ struct EncodeState {
 
 // Codes planes down to klo (inclusive) from the resident half whose first plane is kbase; returns
 // with st.done set when the block is finished, or cleared when it needs planes below klo.
-template <int N>
+// TIGHT: code all runs of a plane in an inner loop instead of one per (warp-wide) iteration - better
+// when planes are noisy and have many runs (reversible mode's residuals), worse for smooth data.
+template <int N, bool TIGHT>
 __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t start, uint32_t budget, int kmin, int klo,
                                                      int kbase, EncodeState& st, const typename PlaneWord<N>::type* sp)
 {
@@ -607,6 +683,7 @@ __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t s
       if (k - 1 < klo)
         break;
       k--;
+      bw.drain_if_low();
       const uint64_t x = sp[(k - kbase) * 32];
       const uint32_t n = pos;  // <= N
       l1 = n < 32 ? n : 32;
@@ -619,19 +696,21 @@ __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t s
     bw.put32(vlo, l1);
     bw.put32(vhi, l2);
     if (r) {
-      const uint32_t z = ctz64(r);  // zeros before the next one-bit
-      pos += z + 1;
-      r = z < 63 ? r >> (z + 1) : 0;
-      const uint32_t explicit_one = pos < N ? 1u : 0u;
-      // the plane's closing '0' test rides along (as an extra zero bit) when this was its last run
-      const uint32_t closing = (!r && pos < N) ? 1u : 0u;
-      if (z < 29)
-        bw.put32(1u | (explicit_one << (z + 1)), z + 1 + explicit_one + closing);
-      else {
-        bw.put32(1, 1);
-        bw.skip(z);
-        bw.put32(explicit_one, explicit_one + closing);
-      }
+      do {
+        const uint32_t z = ctz64(r);  // zeros before the next one-bit
+        pos += z + 1;
+        r = z < 63 ? r >> (z + 1) : 0;
+        const uint32_t explicit_one = pos < N ? 1u : 0u;
+        // the plane's closing '0' test rides along (as an extra zero bit) when this was its last run
+        const uint32_t closing = (!r && pos < N) ? 1u : 0u;
+        if (z < 29)
+          bw.put32(1u | (explicit_one << (z + 1)), z + 1 + explicit_one + closing);
+        else {
+          bw.put32(1, 1);
+          bw.skip(z);
+          bw.put32(explicit_one, explicit_one + closing);
+        }
+      } while (TIGHT && r);
     }
     else if (fresh)
       bw.put32(0, pos < N ? 1u : 0u);  // no new coefficient in this plane: just the '0' test
@@ -712,7 +791,7 @@ struct DecodeState {
   bool done;      // budget exhausted or all planes decoded
 };
 
-template <int N>
+template <int N, bool TIGHT>
 __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, int klo, int kbase, DecodeState& st,
                                                      typename PlaneWord<N>::type* sp)
 {
@@ -730,6 +809,7 @@ __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, 
       if (k - 1 < klo)
         break;
       k--;
+      br.restage_if_low();
     }
     {
       // verbatim bits of a plane that starts now (zero-length reads otherwise: uniform code)
@@ -740,7 +820,9 @@ __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, 
       bits -= m;
       open = true;
     }
-    bool done = true;
+    bool done;
+    do {
+    done = true;
     if (bits && n < N) {
       const uint32_t g = br.peek32();
       if (g & 1u) {
@@ -802,6 +884,7 @@ __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, 
         bits--;
       }
     }
+    } while (TIGHT && !done);
     if (done) {
       sp[(k - kbase) * 32] = (typename PlaneWord<N>::type)x;
       lowest = k;
@@ -1053,17 +1136,17 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     if constexpr (P == 64) {
       to_planes_half<1, UInt, N>(u, sp);
       if (!st.done)
-        encode_planes_staged<N>(bw, start, budget, kmin, 32, 32, st, sp);
+        encode_planes_staged<N, REV>(bw, start, budget, kmin, 32, 32, st, sp);
       if (__any_sync(0xffffffffu, !st.done)) {
         to_planes_half<0, UInt, N>(u, sp);
         if (!st.done)
-          encode_planes_staged<N>(bw, start, budget, kmin, 0, 0, st, sp);
+          encode_planes_staged<N, REV>(bw, start, budget, kmin, 0, 0, st, sp);
       }
     }
     else {
       to_planes_half<0, UInt, N>(u, sp);
       if (!st.done)
-        encode_planes_staged<N>(bw, start, budget, kmin, 0, 0, st, sp);
+        encode_planes_staged<N, REV>(bw, start, budget, kmin, 0, 0, st, sp);
     }
     const uint32_t used = bw.tell() - start;
     bits += used < budget ? used : budget;
@@ -1129,17 +1212,17 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
       u[i] = 0;
     if constexpr (P == 64) {
       if (!st.done)
-        decode_planes_staged<N>(br, kmin, 32, 32, st, sp);
+        decode_planes_staged<N, REV>(br, kmin, 32, 32, st, sp);
       from_planes_half<1, UInt, N>(u, sp, st.lowest);
       if (__any_sync(0xffffffffu, !st.done)) {
         if (!st.done)
-          decode_planes_staged<N>(br, kmin, 0, 0, st, sp);
+          decode_planes_staged<N, REV>(br, kmin, 0, 0, st, sp);
         from_planes_half<0, UInt, N>(u, sp, st.lowest);
       }
     }
     else {
       if (!st.done)
-        decode_planes_staged<N>(br, kmin, 0, 0, st, sp);
+        decode_planes_staged<N, REV>(br, kmin, 0, 0, st, sp);
       from_planes_half<0, UInt, N>(u, sp, st.lowest);
     }
     bits += budget - st.bits;

@@ -216,7 +216,7 @@ constexpr int kStageSlack = 8;    // words of overshoot room: one plane may exce
 constexpr int kStagedPlanes = 32;  // planes resident per phase in the staged kernels (two-phase for 64-bit types)
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? 9 : ZB_MINBLOCKS64)
+__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
 encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      uint64_t* __restrict__ out, uint64_t start_bit)
 {
@@ -267,7 +267,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 constexpr int kReadSlack = 3;  // the window prefetches up to two words past the block and always peeks one more
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? 9 : ZB_MINBLOCKS64)
+__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
 decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      const uint64_t* __restrict__ in, uint64_t start_bit)
 {
@@ -310,6 +310,73 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
 
   StageReader br;
   br.init(stage);
+  typename TR::Scalar v[N];
+  decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  if (valid) {
+    const BlockPos<DIMS> pos = locate<DIMS>(g, b);
+    scatter<DIMS>(v, data, g, pos);
+  }
+}
+
+// Variable rate, fast path.  Encode: same staged coder, but the block's words leave for its
+// scratch slot (the column is a kVarStageWords-word window that is drained at plane boundaries when
+// it runs low) and the coded length is recorded; a scan + compaction pass then places the blocks.
+// Decode: the block starts at an arbitrary bit offset (from the index scan); a window of its words
+// is staged in the column and slid forward at plane boundaries for long blocks.
+constexpr int kVarStageWords = 64;  // 2048 bits: more than almost every variable-rate block
+
+template <int TYPE, int DIMS, bool REV>
+__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
+encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
+                  uint32_t* __restrict__ slots, uint32_t slot_words32, uint16_t* __restrict__ lengths,
+                  uint64_t block0, uint64_t block1)
+{
+  using TR = Traits<TYPE>;
+  constexpr int N = 1 << (2 * DIMS);
+  using PW = typename PlaneWord<N>::type;
+  extern __shared__ uint64_t smem_raw[];
+  constexpr uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + kVarStageWords * 32 * 4;
+  char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
+  PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
+
+  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = b_raw < block1;
+  const uint64_t b = valid ? b_raw : block1 - 1;
+  const BlockPos<DIMS> pos = locate<DIMS>(g, b);
+  typename TR::Scalar v[N];
+  gather<DIMS>(v, data, g, pos);
+
+  StageWriter bw;
+  // lanes past the end write to the last block's slot too; they carry identical bits
+  bw.init(stage, slots + (b - block0) * (uint64_t)slot_words32, kVarStageWords);
+  const uint32_t bits = encode_block<TYPE, DIMS, REV>(v, prm, bw, sp);
+  bw.finish_slot();
+  if (valid)
+    lengths[b] = (uint16_t)bits;
+}
+
+template <int TYPE, int DIMS, bool REV>
+__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
+decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm, const uint32_t* __restrict__ in,
+                  const uint64_t* __restrict__ offsets, const uint16_t* __restrict__ lengths)
+{
+  using TR = Traits<TYPE>;
+  constexpr int N = 1 << (2 * DIMS);
+  using PW = typename PlaneWord<N>::type;
+  extern __shared__ uint64_t smem_raw[];
+  constexpr uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + kVarStageWords * 32 * 4;
+  char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
+  PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
+
+  const uint64_t b_raw = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = b_raw < g.nblocks;
+  const uint64_t b = valid ? b_raw : g.nblocks - 1;
+  const uint64_t off = offsets[b];
+  const uint32_t phase = (uint32_t)(off & 31), len = lengths[b];
+  StageReader br;
+  br.init_var(stage, kVarStageWords, in + (off >> 5), (phase + len + 31) >> 5, phase);
   typename TR::Scalar v[N];
   decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
   if (valid) {

@@ -46,6 +46,7 @@ struct DecodeArgs {
   const void* in;
   uint64_t start_bit;
   const uint64_t* offsets;
+  const uint16_t* lengths;  // OFFS 1: coded length of every block (bounds the staged reads)
   cudaStream_t st;
   int staged;       // OFFS 0 only: use the shared-memory staged fast path when the stream is word aligned
 };
