@@ -652,6 +652,10 @@ __device__ __forceinline__ uint32_t encode_planes(Writer& bw, uint32_t budget, u
 // implied), with the closing '0' folded in when it was the plane's last run.  Lanes whose planes
 // have several runs simply spend more iterations.  The bit budget is enforced by truncation in
 // StageWriter::finish().
+template <class T> __device__ __forceinline__ uint32_t ctz_any(T x);
+template <> __device__ __forceinline__ uint32_t ctz_any<uint32_t>(uint32_t x) { return (uint32_t)__ffs((int)x) - 1; }
+template <> __device__ __forceinline__ uint32_t ctz_any<uint64_t>(uint64_t x) { return ctz64(x); }
+
 struct EncodeState {
   uint64_t r;     // group-tested bits of the current plane still to code (bit 0 = coefficient pos)
   uint32_t pos;   // coefficients settled so far: carries over as the next plane's verbatim count n
@@ -667,7 +671,9 @@ template <int N, bool TIGHT>
 __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t start, uint32_t budget, int kmin, int klo,
                                                      int kbase, EncodeState& st, const typename PlaneWord<N>::type* sp)
 {
-  uint64_t r = st.r;
+  using R = typename PlaneWord<N>::type;  // 32-bit arithmetic suffices for blocks of <= 32 values
+  constexpr uint32_t RB = 8 * sizeof(R);
+  R r = (R)st.r;
   uint32_t pos = st.pos;
   int k = st.k;
   bool done = false;
@@ -684,22 +690,25 @@ __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t s
         break;
       k--;
       bw.drain_if_low();
-      const uint64_t x = sp[(k - kbase) * 32];
+      const R x = sp[(k - kbase) * 32];
       const uint32_t n = pos;  // <= N
       l1 = n < 32 ? n : 32;
-      l2 = n - l1;
       vlo = (uint32_t)x & mask32(l1);
-      vhi = (uint32_t)(x >> 32) & mask32(l2);
-      r = n < 64 ? x >> n : 0;
+      if (N > 32) {
+        l2 = n - l1;
+        vhi = (uint32_t)((uint64_t)x >> 32) & mask32(l2);
+      }
+      r = n < RB ? (R)(x >> n) : (R)0;
       fresh = true;
     }
     bw.put32(vlo, l1);
-    bw.put32(vhi, l2);
+    if (N > 32)
+      bw.put32(vhi, l2);
     if (r) {
       do {
-        const uint32_t z = ctz64(r);  // zeros before the next one-bit
+        const uint32_t z = ctz_any<R>(r);  // zeros before the next one-bit
         pos += z + 1;
-        r = z < 63 ? r >> (z + 1) : 0;
+        r = z < RB - 1 ? (R)(r >> (z + 1)) : (R)0;
         const uint32_t explicit_one = pos < N ? 1u : 0u;
         // the plane's closing '0' test rides along (as an extra zero bit) when this was its last run
         const uint32_t closing = (!r && pos < N) ? 1u : 0u;
@@ -814,8 +823,11 @@ __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, 
     {
       // verbatim bits of a plane that starts now (zero-length reads otherwise: uniform code)
       const uint32_t m = start ? (n < bits ? n : bits) : 0u;
-      const uint32_t l1 = m < 32 ? m : 32, l2 = m - l1;
-      const uint32_t v1 = br.get32(l1), v2 = br.get32(l2);
+      const uint32_t l1 = m < 32 ? m : 32;
+      const uint32_t v1 = br.get32(l1);
+      uint32_t v2 = 0;
+      if (N > 32)
+        v2 = br.get32(m - l1);
       x = start ? ((uint64_t)v1 | ((uint64_t)v2 << 32)) : x;
       bits -= m;
       open = true;
