@@ -101,3 +101,46 @@ def slab_base_bits(local_bits, start_bit=0, group=None):
 def fixed_rate_base_bit(plan, maxbits, start_bit=0):
     """Deterministic slab offset for fixed-rate streams - no communication."""
     return start_bit + plan.blocks_before * maxbits
+
+
+# --------------------------------------------------------------------------------------------------
+# device path: one process per GPU (torch.distributed, NCCL)
+# --------------------------------------------------------------------------------------------------
+def compress_slab_cuda(slab, plan, mode, start_bit=0, group=None):
+    """Compress this rank's slab (a CUDA tensor, plan.slab_shape) and locate it in the global stream.
+
+    Returns (Compressed of the slab encoded at bit 0 of a local buffer, slab bit length, base bit of the
+    slab in the global stream, list of all slab bit lengths or None for fixed rate)."""
+    import zfp_b200
+    from zfp_b200 import api
+    c = zfp_b200.compress(slab, **mode)
+    if api.is_fixed_rate_mode(mode):
+        maxbits = api.mode_params(mode, str(slab.dtype), slab.dim())[1]
+        return c, plan.blocks * maxbits, fixed_rate_base_bit(plan, maxbits, start_bit), None
+    nbits = int(c.stream.index_lengths().astype(np.int64).sum())
+    base, lengths = slab_base_bits(nbits, start_bit, group)
+    return c, nbits, base, lengths
+
+
+def gather_stream_cuda(c, nbits, base, total_bits, group=None):
+    """Assemble the global stream on every rank: all_gather the (padded) slab payloads over NVLink and
+    place each at its base bit with the device bit-copy kernel.  Returns an int64 CUDA tensor of words."""
+    import torch
+    import torch.distributed as dist
+    from zfp_b200 import api
+    world = dist.get_world_size(group)
+    dev = c.words.device
+    meta = torch.tensor([nbits, base], dtype=torch.int64, device=dev)
+    metas = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [[int(v) for v in m.tolist()] for m in metas]
+    max_words = max((m[0] + 63) // 64 for m in metas) + 1
+    mine = torch.zeros(max_words, dtype=torch.int64, device=dev)
+    mine[: (nbits + 63) // 64] = c.words[: (nbits + 63) // 64]
+    parts = [torch.zeros(max_words, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    out = torch.zeros((total_bits + 63) // 64 + 1, dtype=torch.int64, device=dev)
+    for (nb, bs), part in zip(metas, parts):
+        api.bitcopy(out, bs, part, 0, nb)
+    torch.cuda.synchronize()
+    return out
