@@ -187,11 +187,11 @@ def run_ours(args):
         if record: record[2].record()
         return c
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         c = step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = zb.launch_count()
     t_begin = torch.cuda.Event(enable_timing=True)
@@ -266,11 +266,15 @@ def run_ours(args):
     values = x.numel()
     enc_alg = values * (8 + RATE / 8.0)   # bytes: read fp64 + write RATE bits per value
     dec_alg = enc_alg
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on this exact workload, from the ncu
+    # --set full captures summarised in profiles/ (a profiler run, not this run)
     roof_enc = {"kernel": "encode_staged_kernel<double,3>", "bound": "hbm", "achieved": enc_alg / (enc_ms * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src, "ms": enc_ms}
+                "peak": peak, "unit": "GB/s", "traffic": 9.6633e9, "traffic_source": "profiles/r1_encode_staged_fp64_r8_1024cubed.md",
+                "algorithmic_bytes": enc_alg, "peak_source": peak_src, "ms": enc_ms}
     roof_enc["frac"] = roof_enc["achieved"] / peak
     roof_dec = {"kernel": "decode_staged_kernel<double,3>", "bound": "hbm", "achieved": dec_alg / (dec_ms * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "traffic": None, "peak_source": peak_src, "ms": dec_ms}
+                "peak": peak, "unit": "GB/s", "traffic": 10.4102e9, "traffic_source": "profiles/r1_decode_staged_fp64_r8_1024cubed.md",
+                "algorithmic_bytes": dec_alg, "peak_source": peak_src, "ms": dec_ms}
     roof_dec["frac"] = roof_dec["achieved"] / peak
     dominant = roof_dec if dec_ms >= enc_ms else roof_enc
 

@@ -323,6 +323,35 @@ class Reference:
         L.stream_close(bs)
         return nbytes
 
+    def decompress_with_header(self, data):
+        """What the reference's zfpy.decompress_numpy does (python/zfpy.pyx:300-340): read the full
+        header, size the array from it, decompress serially."""
+        L = self.L
+        L.zfp_field_size.restype = C.c_size_t
+        L.zfp_field_size.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+        L.zfp_field_type.restype = C.c_int
+        L.zfp_field_type.argtypes = [C.c_void_p]
+        L.zfp_field_dimensionality.restype = C.c_uint
+        L.zfp_field_dimensionality.argtypes = [C.c_void_p]
+        words = np.zeros((len(data) + 15) // 8 + 1, dtype=np.uint64)
+        words.view(np.uint8)[: len(data)] = np.frombuffer(data, dtype=np.uint8)
+        bs = L.stream_open(words.ctypes.data, words.nbytes)
+        z = L.zfp_stream_open(bs)
+        f = L.zfp_field_alloc()
+        assert L.zfp_read_header(z, f, 7), "reference could not read the header"
+        dims = L.zfp_field_dimensionality(f)
+        size = (C.c_size_t * 4)()
+        L.zfp_field_size(f, size)
+        shape = tuple(reversed([int(size[i]) for i in range(dims)]))
+        inv = {v: k for k, v in ZFP_TYPE.items()}
+        out = np.empty(shape, dtype=inv[L.zfp_field_type(f)])
+        L.zfp_field_set_pointer(f, out.ctypes.data)
+        nbytes = L.zfp_decompress(z, f)
+        L.zfp_field_free(f)
+        L.zfp_stream_close(z)
+        L.stream_close(bs)
+        return out, nbytes
+
     def compress(self, a, policy=0, threads=0, **mode):
         a = np.ascontiguousarray(a)
         words, _ = self.compress_raw(a.reshape(-1), 0, a.dtype, _shape_to_n(a.shape), None, mode,

@@ -229,3 +229,36 @@ def test_reference_library_with_our_backend_as_its_cuda_policy(port):
             assert L.zfp_decompress(z, f) == cuda.nbytes
             L.zfp_field_free(f); L.zfp_stream_close(z); L.stream_close(bs)
             assert out.tobytes() == R.decompress(serial, a.shape, a.dtype, **mode).tobytes()
+
+
+def test_zfpy_compatible_module_interoperates_with_reference(zb, ref):
+    """zfp_b200.zfpy: same signatures and byte format as the reference's zfpy (python/zfpy.pyx);
+    streams with full headers travel both ways, with and without our index trailer."""
+    from zfp_b200 import zfpy
+    for dtype, shape in ((np.float64, (30, 40, 50)), (np.float32, (100, 90)), (np.int32, (24, 24, 24)), (np.float64, (12, 10, 9, 8))):
+        a = make_field(shape, dtype, seed=41, kind="smooth")
+        n = list(reversed(shape)) + [0] * (4 - len(shape))
+        for kw, mode in (({"rate": 8}, {"rate": 8}), ({"tolerance": 1e-3}, {"accuracy": 1e-3}), ({"precision": 16}, {"precision": 16}), ({}, {"reversible": True})):
+            if np.dtype(dtype).kind != "f" and "tolerance" in kw:
+                continue
+            ours = zfpy.compress_numpy(a, **kw)
+            theirs, _ = ref.compress_raw(a.reshape(-1), 0, dtype, n, None, mode, header_mask=7)
+            assert ours == theirs.tobytes(), (shape, kw)                 # identical bytes incl. header
+            back_ref, used = ref.decompress_with_header(ours)           # the reference reads ours
+            assert used == len(ours)
+            back_ours = zfpy.decompress_numpy(theirs.tobytes())          # we read the reference's
+            assert back_ours.shape == a.shape and back_ours.dtype == a.dtype
+            assert back_ours.tobytes() == back_ref.tobytes()
+            with_index = zfpy.compress_numpy(a, index_trailer=True, **kw)
+            assert with_index[: len(ours)] == ours
+            assert zfpy.decompress_numpy(with_index).tobytes() == back_ref.tobytes()
+            back_ref2, _ = ref.decompress_with_header(with_index)       # trailer is invisible to zfp readers
+            assert back_ref2.tobytes() == back_ref.tobytes()
+            if not kw:
+                assert back_ours.tobytes() == a.tobytes()
+    import torch
+    x = torch.from_numpy(make_field((20, 24, 28), np.float64, seed=5, kind="smooth")).cuda()
+    buf, c = zfpy.compress_tensor(x, tolerance=1e-4)
+    assert bytes(buf.cpu().numpy()[:4]) == b"zfp\x05"
+    y = zfpy.decompress_tensor(c)
+    assert float((x - y).abs().max()) <= 1e-4
