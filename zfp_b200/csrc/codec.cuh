@@ -704,25 +704,29 @@ __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t s
     bw.put32(vlo, l1);
     if (N > 32)
       bw.put32(vhi, l2);
-    if (r) {
-      do {
-        const uint32_t z = ctz_any<R>(r);  // zeros before the next one-bit
-        pos += z + 1;
-        r = z < RB - 1 ? (R)(r >> (z + 1)) : (R)0;
-        const uint32_t explicit_one = pos < N ? 1u : 0u;
-        // the plane's closing '0' test rides along (as an extra zero bit) when this was its last run
-        const uint32_t closing = (!r && pos < N) ? 1u : 0u;
-        if (z < 29)
-          bw.put32(1u | (explicit_one << (z + 1)), z + 1 + explicit_one + closing);
-        else {
-          bw.put32(1, 1);
-          bw.skip(z);
-          bw.put32(explicit_one, explicit_one + closing);
-        }
-      } while (TIGHT && r);
-    }
-    else if (fresh)
-      bw.put32(0, pos < N ? 1u : 0u);  // no new coefficient in this plane: just the '0' test
+    do {
+      // one group-tested item with a single append: a run ('1', z zeros, '1' - implied on the last
+      // coefficient - plus the plane's closing '0' test when it was the last run), or the lone '0'
+      // test of a plane without new coefficients
+      const bool run = r != 0;
+      const uint32_t z = run ? ctz_any<R>(r) : 0u;  // zeros before the next one-bit
+      const uint32_t pos1 = run ? pos + z + 1 : pos;
+      const R r1 = (run && z < RB - 1) ? (R)(r >> (z + 1)) : (R)0;
+      const uint32_t explicit_one = pos1 < N ? 1u : 0u;
+      const uint32_t closing = (run && !r1 && pos1 < N) ? 1u : 0u;
+      if (run && z >= 29) {
+        bw.put32(1, 1);
+        bw.skip(z);
+        bw.put32(explicit_one, explicit_one + closing);
+      }
+      else {
+        const uint32_t v = run ? (1u | (explicit_one << (z + 1))) : 0u;
+        const uint32_t len = run ? z + 1 + explicit_one + closing : ((fresh && pos < N) ? 1u : 0u);
+        bw.put32(v, len);
+      }
+      pos = pos1;
+      r = r1;
+    } while (TIGHT && r);
   }
   st.r = r;
   st.pos = pos;
@@ -834,68 +838,62 @@ __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, 
     }
     bool done;
     do {
-    done = true;
-    if (bits && n < N) {
+      // One group-tested item, branch-free in the common cases: all quantities are derived from a
+      // single 32-bit look at the stream and consumed with ONE skip.
+      const bool active = bits && n < N;
       const uint32_t g = br.peek32();
-      if (g & 1u) {
-        // positive group test: zeros up to the next one-bit, the last coefficient or the budget
-        const uint32_t avail = bits - 1;
-        const uint32_t room = N - 1 - n;
-        const uint32_t lim = avail < room ? avail : room;
-        const bool found = (g >> 1) != 0;  // a one-bit is visible among the next 31 bits
-        const uint32_t z = found ? (uint32_t)__ffs((int)(g >> 1)) - 1 : 31u;
-        if (found && z < lim) {
-          br.skip32(z + 2);  // test, z zeros, one
-          bits -= z + 2;
-          n += z;
-        }
-        else if (lim <= 31) {
-          br.skip32(lim + 1);  // test and lim zeros; the one-bit is implied / the budget ran out
-          bits -= lim + 1;
-          n += lim;
-        }
-        else {
-          // more than 31 zeros in a row: keep scanning a window at a time
-          br.skip32(32);
-          bits -= 32;
-          n += 31;
-          uint32_t left = lim - 31;
-          for (;;) {
-            const uint32_t w = br.peek32();
-            const uint32_t step = left < 32 ? left : 32;
-            const uint32_t zz = w ? (uint32_t)__ffs((int)w) - 1 : 32u;
-            if (zz < step) {
-              br.skip32(zz + 1);
-              bits -= zz + 1;
-              n += zz;
-              break;
-            }
-            br.skip32(step);
-            bits -= step;
-            n += step;
-            left -= step;
-            if (!left)
-              break;
+      const bool positive = active && (g & 1u);
+      const uint32_t avail = bits - 1;                       // budget after the test bit
+      const uint32_t room = N - 1 - n;                        // zeros that may precede the one-bit
+      const uint32_t lim = avail < room ? avail : room;
+      const uint32_t gg = g >> 1;
+      const bool found = gg != 0;                             // a one-bit is visible in the window
+      const uint32_t z = found ? (uint32_t)__ffs((int)gg) - 1 : 31u;
+      const bool hit = found && z < lim;                      // an explicit one-bit ends the run
+      if (positive && !hit && lim > 31) {
+        // more than 31 zeros in a row: keep scanning a window at a time (rare)
+        br.skip32(32);
+        bits -= 32;
+        n += 31;
+        uint32_t left = lim - 31;
+        for (;;) {
+          const uint32_t w = br.peek32();
+          const uint32_t step = left < 32 ? left : 32;
+          const uint32_t zz = w ? (uint32_t)__ffs((int)w) - 1 : 32u;
+          if (zz < step) {
+            br.skip32(zz + 1);
+            bits -= zz + 1;
+            n += zz;
+            break;
           }
+          br.skip32(step);
+          bits -= step;
+          n += step;
+          left -= step;
+          if (!left)
+            break;
         }
         x |= 1ull << n;
         n++;
-        // the plane goes on if coefficients and budget remain and the next test is positive;
-        // a negative test closes it and is consumed here
-        if (bits && n < N) {
-          if (br.peek32() & 1u)
-            done = false;
-          else {
-            br.skip32(1);
-            bits--;
-          }
-        }
+        done = !(bits && n < N);  // a following test bit, positive or negative, is the next item
       }
       else {
-        br.skip32(1);
-        bits--;
+        const uint32_t c = hit ? z : lim;                     // zeros read (then the one-bit, the last
+                                                              // coefficient or the end of the budget)
+        uint32_t t = positive ? 1 + c + (hit ? 1u : 0u) : (active ? 1u : 0u);
+        const uint32_t n1 = positive ? n + c + 1 : n;
+        x |= positive ? 1ull << ((n + c) & 63) : 0ull;        // deposited even if the scan ran dry
+        const uint32_t bits1 = bits - t;
+        // the plane goes on if coefficients and budget remain; a negative test that is visible in
+        // the same window closes it here, anything else is the next item
+        const bool more = positive && bits1 && n1 < N;
+        const bool closes = more && t < 32 && !((g >> (t & 31)) & 1u);
+        t += closes ? 1u : 0u;
+        br.skip32(t);
+        bits = bits1 - (closes ? 1u : 0u);
+        n = n1;
+        done = !more || closes;
       }
-    }
     } while (TIGHT && !done);
     if (done) {
       sp[(k - kbase) * 32] = (typename PlaneWord<N>::type)x;
