@@ -233,6 +233,63 @@ struct StageWriter {
   }
 };
 
+// PTX shifts clamp the shift amount at the register width (a shift by >= width gives 0), which is
+// exactly what the coder wants at n == N; C++ shifts leave that case undefined.
+__device__ __forceinline__ uint64_t shr64c(uint64_t x, uint32_t n) { uint64_t r; asm("shr.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint64_t shl64c(uint64_t x, uint32_t n) { uint64_t r; asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t shr32c(uint32_t x, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+__device__ __forceinline__ uint32_t shl32c(uint32_t x, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
+
+// Column writer (plane-lockstep fixed-rate path): same lane-private [word][lane] column as
+// StageWriter, addressed by bit position.  An append ORs the value into the partial word kept in
+// `acc` and stores every word the value can touch UNCONDITIONALLY (a later append rewrites the
+// partial word with more bits in it): no predicates, no flush test, and the word holding `bp` is
+// always current in shared memory.  Words beyond it hold zeros or were never written; finish()
+// zero-fills up to the block size and the kernel copies exactly that many words (truncation).
+struct ColWriter {
+  static constexpr bool kStaged = true;
+  static constexpr bool kLockstep = true;
+  uint32_t* col;  // word 0 of this lane's column (words are 32 elements apart)
+  uint32_t acc;   // bits of the word containing bp that lie below bp
+  uint32_t bp;    // bits appended so far
+
+  __device__ __forceinline__ void init(uint32_t* column) { col = column; acc = 0; bp = 0; }
+  __device__ __forceinline__ void append32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
+  {
+    const uint32_t sh = bp & 31;
+    uint32_t* w = col + (bp & ~31u);
+    const uint32_t a0 = acc | (v << sh);
+    const uint32_t a1 = __funnelshift_l(v, 0, sh);
+    w[0] = a0;
+    w[32] = a1;
+    acc = sh + len < 32 ? a0 : a1;
+    bp += len;
+  }
+  __device__ __forceinline__ void append64(uint32_t lo, uint32_t hi, uint32_t len)  // (hi:lo) < 2^len, len <= 64
+  {
+    const uint32_t sh = bp & 31;
+    uint32_t* w = col + (bp & ~31u);
+    const uint32_t a0 = acc | (lo << sh);
+    const uint32_t a1 = __funnelshift_l(lo, hi, sh);
+    const uint32_t a2 = __funnelshift_l(hi, 0, sh);
+    w[0] = a0;
+    w[32] = a1;
+    w[64] = a2;
+    const uint32_t t = sh + len;  // <= 95
+    acc = t < 32 ? a0 : (t < 64 ? a1 : a2);
+    bp += len;
+  }
+  __device__ __forceinline__ void put(uint64_t v, uint32_t len) { append64((uint32_t)v, (uint32_t)(v >> 32), len); }
+  __device__ __forceinline__ void pad(uint32_t) {}  // finish() zero-fills
+  __device__ __forceinline__ uint32_t tell() const { return bp; }
+  // close the block at exactly total_words 32-bit words: zero-fill; overshoot is simply not copied
+  __device__ __forceinline__ void finish(uint32_t total_words)
+  {
+    for (uint32_t w = (bp >> 5) + 1; w < total_words; w++)
+      col[w * 32] = 0;
+  }
+};
+
 // bit reader with a 64-bit look-ahead window
 struct BitReader {
   static constexpr bool kStaged = false;
@@ -734,6 +791,101 @@ __device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t s
   st.done = done;
 }
 
+// Plane-lockstep coder for the column writer.  All 32 lanes walk the planes together (k is warp
+// uniform); per plane a lane appends the n verbatim bits in one go, then the whole group-tested
+// part T as one word.  T is the region y = x >> n with a flag bit inserted after every one-bit
+// ("is there another one above?") behind a leading test bit; the last flag is the plane's closing
+// '0' test, and a one-bit on the last coefficient is implied together with its flag
+// (encode.c:108-124).  With Y' = y's one-bits each moved up by its rank, the doubled string is
+// Y' | Y' << 1 = 3 Y'; Y' is built by peeling the lowest one-bit per step with a warp-uniform shift
+// count.  Planes whose T does not fit 32 bits (noisy data) take a per-lane run loop instead.
+struct LockState {
+  uint32_t pos;   // coefficients settled so far = verbatim count of the next plane
+  int k;          // last plane coded (starts at P), warp uniform
+  bool done;      // budget exhausted or below the block's precision
+};
+
+template <int N>
+__device__ __forceinline__ void encode_planes_lockstep(ColWriter& bw, uint32_t limit, int kmin, int klo, int kbase,
+                                                       LockState& st, const typename PlaneWord<N>::type* sp)
+{
+  using R = typename PlaneWord<N>::type;
+  constexpr uint32_t FULL = 0xffffffffu;
+  uint32_t pos = st.pos;
+  bool done = st.done;
+  int k = st.k;
+  while (k > klo && __any_sync(FULL, !done)) {
+    k--;
+    done = done || k < kmin || bw.bp >= limit;
+    const R x = sp[(k - kbase) * 32];
+    const uint32_t n = done ? 0u : pos;  // a finished lane appends nothing: zero-length verbatim part, empty T
+    R r, verb;
+    if constexpr (N > 32) {
+      r = shr64c(x, n);
+      verb = x ^ shl64c(r, n);
+    }
+    else {
+      r = shr32c(x, n);
+      verb = x ^ shl32c(r, n);
+    }
+    const R y = done ? (R)0 : r;
+    const bool test = !done && n < N;
+    const uint32_t y32 = (uint32_t)y;
+    const uint32_t c = (uint32_t)__popc(y32);
+    const int msb = 31 - __clz((int)y32);  // -1 when y32 == 0
+    bool slow = false;
+    if constexpr (N > 32)
+      slow = (uint32_t)((uint64_t)y >> 32) != 0 || msb + (int)c + 2 > 32;
+    if (N <= 32 || !__any_sync(FULL, slow)) {
+      uint32_t yp = 0, rem = y32;
+      const uint32_t cmax = __reduce_max_sync(FULL, c);
+      for (uint32_t i = 0; i < cmax; i++) {
+        const uint32_t t = rem & (0u - rem);
+        yp |= t << i;
+        rem ^= t;
+      }
+      const bool has = y32 != 0;
+      const uint32_t top = n + (uint32_t)(msb + 1);    // coefficients settled after this plane
+      const uint32_t last = (has && top == N) ? 1u : 0u;
+      const uint32_t keep = (uint32_t)msb + c - last;   // msb + 1 + c flags and bits, minus the closing flag (and the implied pair)
+      const uint32_t e = (yp * 3u) & mask32(keep);
+      const uint32_t tval = has ? (1u | (e << 1)) : 0u;
+      const uint32_t tlen = has ? keep + 2 - last : (test ? 1u : 0u);
+      pos = has ? top : pos;
+      if constexpr (N > 32)
+        bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
+      else
+        bw.append32((uint32_t)verb, n);
+      bw.append32(tval, tlen);
+    }
+    else {
+      if constexpr (N > 32)
+        bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
+      else
+        bw.append32((uint32_t)verb, n);
+      if (test) {
+        R rr = y;
+        uint32_t p = n;
+        while (rr) {
+          const uint32_t z = ctz_any<R>(rr);
+          const uint32_t p1 = p + z + 1;
+          const uint64_t ex = p1 < N ? 1u : 0u;           // the one-bit is implied on the last coefficient
+          const uint64_t v = 1ull | shl64c(ex, z + 1);    // '1', z zeros, '1'
+          bw.append64((uint32_t)v, (uint32_t)(v >> 32), z + 1 + (uint32_t)ex);
+          rr = (R)shr64c((uint64_t)rr, z + 1);
+          p = p1;
+        }
+        if (p < N)
+          bw.append32(0, 1);  // closing (or only) group test
+        pos = p;
+      }
+    }
+  }
+  st.pos = pos;
+  st.done = done;
+  st.k = k;
+}
+
 // Mirror image.  Decoded planes are stored to sp[k*32]; returns bits consumed and, through
 // kstop, the lowest plane index that was written.
 template <int N, int P>
@@ -1033,6 +1185,9 @@ __device__ __forceinline__ typename std::make_signed<UInt>::type uint2int(UInt u
   return (typename std::make_signed<UInt>::type)((u ^ mask) - mask);
 }
 
+template <class W, class = void> struct is_lockstep : std::false_type {};
+template <class W> struct is_lockstep<W, std::enable_if_t<W::kLockstep>> : std::true_type {};
+
 // ------------------------------------------------------------------------------------------------
 // whole-block encode / decode for one thread.  `sp` is the lane's plane column in shared memory.
 // Returns the number of bits the block occupies in the stream.
@@ -1137,7 +1292,27 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     }
     maxprec = prec;
   }
-  if constexpr (Writer::kStaged) {
+  if constexpr (is_lockstep<Writer>::value) {
+    // plane-lockstep coder (fixed rate, column writer); two-phase like the staged path below
+    const uint32_t budget = prm.maxbits - bits, start = bw.tell();
+    const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+    LockState st = { 0, P, !coded };
+    if constexpr (P == 64) {
+      to_planes_half<1, UInt, N>(u, sp);
+      encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+      if (__any_sync(0xffffffffu, !st.done)) {
+        to_planes_half<0, UInt, N>(u, sp);
+        encode_planes_lockstep<N>(bw, start + budget, kmin, 0, 0, st, sp);
+      }
+    }
+    else {
+      to_planes_half<0, UInt, N>(u, sp);
+      encode_planes_lockstep<N>(bw, start + budget, kmin, 0, 0, st, sp);
+    }
+    const uint32_t used = bw.tell() - start;
+    bits += used < budget ? used : budget;
+  }
+  else if constexpr (Writer::kStaged) {
     // two-phase: the high 32 planes first; the low 32 only if some block of the warp still has
     // budget when it gets there (all 32 lanes reach the vote: the staged kernel has no early exit)
     const uint32_t budget = prm.maxbits - bits, start = bw.tell();

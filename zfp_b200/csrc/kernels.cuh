@@ -11,7 +11,10 @@
 
 namespace zb {
 
-constexpr int kThreads = 64;  // threads per CTA for the codec kernels (2 warps: more CTAs fit the shared-memory budget)
+#ifndef ZB_THREADS
+#define ZB_THREADS 64
+#endif
+constexpr int kThreads = ZB_THREADS;  // threads per CTA for the codec kernels (2 warps: more CTAs fit the shared-memory budget)
 
 // ------------------------------------------------------------------------------------------------
 // block <-> array
@@ -212,7 +215,7 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_MINBLOCKS64
 #define ZB_MINBLOCKS64 5  // launch-bounds hint for the 64-bit staged kernels; 5 measured best of {4,5,6,8} on B200
 #endif
-constexpr int kStageSlack = 8;    // words of overshoot room: one plane may exceed the budget by < 200 bits
+constexpr int kStageSlack = 10;   // words of overshoot room: a plane may exceed the budget by < 200 bits and an append stores two words ahead
 constexpr int kStagedPlanes = 32;  // planes resident per phase in the staged kernels (two-phase for 64-bit types)
 
 template <int TYPE, int DIMS, bool REV>
@@ -239,7 +242,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   typename TR::Scalar v[N];
   gather<DIMS>(v, data, g, pos);
 
-  StageWriter bw;
+  ColWriter bw;
   bw.init(stage);
   encode_block<TYPE, DIMS, REV>(v, prm, bw, sp);
   bw.finish(words);
