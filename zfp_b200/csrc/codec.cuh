@@ -425,6 +425,38 @@ struct StageReader {
   }
 };
 
+// Column reader (plane-lockstep fixed-rate path): the block's words sit in a lane-private
+// [word][lane] column followed by zero words; reads are by bit position straight from shared memory
+// (no register window to maintain), so all loads of a plane are issued together.
+struct ColReader {
+  static constexpr bool kStaged = true;
+  static constexpr bool kLockstep = true;
+  const uint32_t* col;
+  uint32_t bp;  // bits consumed so far
+
+  __device__ __forceinline__ void init(const uint32_t* column) { col = column; bp = 0; }
+  __device__ __forceinline__ uint32_t peek32(uint32_t pos) const  // the 32 bits starting at bit `pos`
+  {
+    const uint32_t* w = col + (pos & ~31u);
+    return __funnelshift_r(w[0], w[32], pos);  // shift amount is taken modulo 32
+  }
+  __device__ __forceinline__ void peek64(uint32_t pos, uint32_t& lo, uint32_t& hi) const
+  {
+    const uint32_t* w = col + (pos & ~31u);
+    const uint32_t w0 = w[0], w1 = w[32], w2 = w[64];
+    lo = __funnelshift_r(w0, w1, pos);
+    hi = __funnelshift_r(w1, w2, pos);
+  }
+  __device__ __forceinline__ uint64_t get(uint32_t len)  // len <= 64
+  {
+    uint32_t lo, hi;
+    peek64(bp, lo, hi);
+    bp += len;
+    const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
+    return v ^ shl64c(shr64c(v, len), len);
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
 // lifting transforms on register-resident values (wrapping arithmetic via unsigned types)
 // ------------------------------------------------------------------------------------------------
@@ -1062,6 +1094,130 @@ __device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, 
   st.done = finished;
 }
 
+// Plane-lockstep decoder for the column reader, the mirror image of encode_planes_lockstep.  Per
+// plane a lane reads its m = min(n, bits) verbatim bits in one go, then parses the whole
+// group-tested part T from one 32-bit look at the stream without a loop over its items: with a
+// virtual one-bit in front, T is a sequence of runs of ones in which data bits and flag bits
+// alternate, starting with a data bit, and T ends after the first run of odd length (its last
+// data bit is followed by a '0' flag).  Run ends come from the carries of W + (run starts), split
+// by the parity of the start position; the data bits are then moved down by 2 + rank to give the
+// region y.  Anything the shortcut cannot prove exact - T longer than the window, the bit budget
+// running out inside T, a scan that reaches the last coefficient (implied one-bit, decode.c:103-111)
+// - sends the warp through the exact per-item loop for that plane.
+struct LockDecodeState {
+  uint32_t bits;  // budget left
+  uint32_t n;     // coefficients significant so far
+  int k;          // last plane decoded (starts at P), warp uniform
+  int lowest;     // lowest plane stored by this lane (P when none)
+  bool done;
+};
+
+template <int N>
+__device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, int klo, int kbase, LockDecodeState& st,
+                                                       typename PlaneWord<N>::type* sp)
+{
+  using R = typename PlaneWord<N>::type;
+  constexpr uint32_t FULL = 0xffffffffu;
+  uint32_t bits = st.bits, n = st.n;
+  int k = st.k, lowest = st.lowest;
+  bool done = st.done;
+  while (k > klo && __any_sync(FULL, !done)) {
+    k--;
+    done = done || k < kmin || bits == 0;
+    const uint32_t m = done ? 0u : (n < bits ? n : bits);  // verbatim bits
+    const uint32_t tp = br.bp + m;                         // where T starts
+    R verb;
+    if constexpr (N > 32) {
+      uint32_t lo, hi;
+      br.peek64(br.bp, lo, hi);
+      const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
+      verb = v ^ shl64c(shr64c(v, m), m);
+    }
+    else {
+      const uint32_t v = br.peek32(br.bp);
+      verb = v ^ shl32c(shr32c(v, m), m);
+    }
+    const uint32_t w = br.peek32(tp);
+    const uint32_t left = bits - m;                        // budget at T (m <= bits)
+    const bool test = !done && n < N && left != 0;
+    // parse T: W' = virtual data bit, then the stream
+    const uint32_t wv = (w << 1) | 1u;
+    const uint32_t s = wv & ~(wv << 1);                    // run starts
+    const uint32_t ae = wv + (s & 0x55555555u), ao = wv + (s & 0xaaaaaaaau);
+    const uint32_t term = (ae & ~wv & 0xaaaaaaaau) | (ao & ~wv & 0x55555555u);  // just past each odd-length run
+    const uint32_t tpos = (uint32_t)__ffs((int)term) - 1;  // bits of T (0xffffffff when no end in the window)
+    uint32_t d = ((wv & ~ae & 0x55555554u) | (wv & ~ao & 0xaaaaaaaau)) & mask32(tpos);  // data bits of T, virtual one dropped
+    d = test ? d : 0u;
+    const uint32_t c = (uint32_t)__popc(d);
+    const uint32_t ntop = n + (uint32_t)(31 - __clz((int)d)) - c;  // n + (msb(d) - 2 - (c-1)) + 1: coefficients settled if c > 0
+    const bool slow = test && (term == 0 || tpos > left || (c != 0 && ntop > N - 1));
+    R x;
+    if (!__any_sync(FULL, slow)) {
+      uint32_t y = 0, rem = d;
+      const uint32_t cmax = __reduce_max_sync(FULL, c);
+      for (uint32_t i = 0; i < cmax; i++) {
+        const uint32_t t = rem & (0u - rem);
+        y |= t >> (i + 2);
+        rem ^= t;
+      }
+      if constexpr (N > 32)
+        x = verb | shl64c((uint64_t)y, n);
+      else
+        x = verb | shl32c(y, n);
+      const uint32_t used = test ? tpos : 0u;
+      bits = left - used;
+      br.bp = tp + used;
+      n = c ? ntop : n;
+    }
+    else {
+      // exact per-item loop (decode.c:96-117) on this plane for every lane
+      x = verb;
+      uint32_t b = left, nn = n, p = tp;
+      if (!done) {
+        while (b && nn < N) {
+          const uint32_t g0 = br.peek32(p);
+          b--;
+          p++;
+          if (!(g0 & 1u))
+            break;
+          const uint32_t room = N - 1 - nn;
+          const uint32_t lim = b < room ? b : room;       // bits the unary scan may read
+          uint32_t taken = 0, g = g0 >> 1, avail = 31;
+          while (taken < lim) {
+            const uint32_t step = lim - taken < avail ? lim - taken : avail;
+            const uint32_t gz = g ? (uint32_t)__ffs((int)g) - 1 : 32u;
+            if (gz < step) {
+              taken += gz + 1;  // gz zeros and the one-bit
+              nn += gz;
+              break;
+            }
+            taken += step;
+            nn += step;
+            g = br.peek32(p + taken);
+            avail = 32;
+          }
+          p += taken;
+          b -= taken;
+          x |= (R)1 << (nn & (8 * sizeof(R) - 1));  // deposited even if the scan ran dry (nn <= N-1)
+          nn++;
+        }
+      }
+      bits = b;
+      br.bp = p;
+      n = nn;
+    }
+    if (!done) {
+      sp[(k - kbase) * 32] = x;
+      lowest = k;
+    }
+  }
+  st.bits = bits;
+  st.n = n;
+  st.k = k;
+  st.lowest = lowest;
+  st.done = done;
+}
+
 // ------------------------------------------------------------------------------------------------
 // floating-point helpers
 // ------------------------------------------------------------------------------------------------
@@ -1388,7 +1544,28 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   }
 
   UInt u[N];
-  if constexpr (Reader::kStaged) {
+  if constexpr (is_lockstep<Reader>::value) {
+    const uint32_t budget = prm.maxbits - bits;
+    const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+    LockDecodeState st = { budget, 0, P, P, zero };
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      u[i] = 0;
+    if constexpr (P == 64) {
+      decode_planes_lockstep<N>(br, kmin, 32, 32, st, sp);
+      from_planes_half<1, UInt, N>(u, sp, st.lowest);
+      if (__any_sync(0xffffffffu, !st.done)) {
+        decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);
+        from_planes_half<0, UInt, N>(u, sp, st.lowest);
+      }
+    }
+    else {
+      decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);
+      from_planes_half<0, UInt, N>(u, sp, st.lowest);
+    }
+    bits += budget - st.bits;
+  }
+  else if constexpr (Reader::kStaged) {
     const uint32_t budget = prm.maxbits - bits;
     const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
     DecodeState st = { 0, budget, 0, P, P, false, zero };

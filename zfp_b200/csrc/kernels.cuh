@@ -267,7 +267,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 // Fixed rate, word-aligned blocks, fast path: each lane first copies its block's words to a
 // shared-memory column (all loads in flight at once instead of one dependent global load per
 // word inside the serial decoder), then decodes from there (StageReader).
-constexpr int kReadSlack = 3;  // the window prefetches up to two words past the block and always peeks one more
+constexpr int kReadSlack = 5;  // zero words after the block: a plane's reads reach 64 + 32 bits past the position, rounded up to words
 
 template <int TYPE, int DIMS, bool REV>
 __global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
@@ -307,11 +307,11 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
       stage[(w + 1) * 32] = (uint32_t)(v >> 32);
     }
   }
-  stage[words * 32] = 0;
-  stage[(words + 1) * 32] = 0;
-  stage[(words + 2) * 32] = 0;
+#pragma unroll
+  for (int j = 0; j < kReadSlack; j++)
+    stage[(words + j) * 32] = 0;
 
-  StageReader br;
+  ColReader br;
   br.init(stage);
   typename TR::Scalar v[N];
   decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
