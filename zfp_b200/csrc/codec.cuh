@@ -838,80 +838,86 @@ struct LockState {
 };
 
 template <int N>
+__device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t limit, int kmin, int k, uint32_t& pos, bool& done,
+                                                      const typename PlaneWord<N>::type x)
+{
+  using R = typename PlaneWord<N>::type;
+  constexpr uint32_t FULL = 0xffffffffu;
+  done = done || k < kmin || bw.bp >= limit;
+  const uint32_t n = done ? 0u : pos;  // a finished lane appends nothing: zero-length verbatim part, empty T
+  R r, verb;
+  if constexpr (N > 32) {
+    r = shr64c(x, n);
+    verb = x ^ shl64c(r, n);
+  }
+  else {
+    r = shr32c(x, n);
+    verb = x ^ shl32c(r, n);
+  }
+  const R y = done ? (R)0 : r;
+  const bool test = !done && n < N;
+  const uint32_t y32 = (uint32_t)y;
+  const uint32_t c = (uint32_t)__popc(y32);
+  const int msb = 31 - __clz((int)y32);  // -1 when y32 == 0
+  // one-bits of the region above its lowest 1, 2, 3, 4 ones
+  const uint32_t r1 = y32 & (y32 - 1), r2 = r1 & (r1 - 1), r3 = r2 & (r2 - 1), r4 = r3 & (r3 - 1);
+  bool slow = false;
+  if constexpr (N > 32)
+    slow = (uint32_t)((uint64_t)y >> 32) != 0 || msb + (int)c + 2 > 32;
+  if constexpr (N > 32)
+    bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
+  else
+    bw.append32((uint32_t)verb, n);
+  // every one-bit moved up by its rank: b0 + 2 b1 + 4 b2 + 8 b3 + ... = y + r1 + 2 r2 + 4 r3 + ...
+  uint32_t yp = y32 + r1 + 2 * r2 + 4 * r3;
+  if (__any_sync(FULL, r4 != 0)) {
+    const uint32_t r5 = r4 & (r4 - 1), r6 = r5 & (r5 - 1), r7 = r6 & (r6 - 1), r8 = r7 & (r7 - 1);
+    yp += 8 * r4 + 16 * r5 + 32 * r6 + 64 * r7;
+    slow = slow || r8 != 0;
+  }
+  if (!__any_sync(FULL, slow)) {
+    const bool has = y32 != 0;
+    const uint32_t top = n + (uint32_t)(msb + 1);    // coefficients settled after this plane
+    const uint32_t last = (has && top == N) ? 1u : 0u;
+    const uint32_t keep = (uint32_t)msb + c - last;   // bits + flags, minus the closing flag (and the implied pair)
+    const uint32_t e = (yp * 3u) & mask32(keep);
+    const uint32_t tval = has ? (1u | (e << 1)) : 0u;
+    const uint32_t tlen = has ? keep + 2 - last : (test ? 1u : 0u);
+    pos = has ? top : pos;
+    bw.append32(tval, tlen);
+  }
+  else if (test) {
+    R rr = y;
+    uint32_t p = n;
+    while (rr) {
+      const uint32_t z = ctz_any<R>(rr);
+      const uint32_t p1 = p + z + 1;
+      const uint64_t ex = p1 < N ? 1u : 0u;           // the one-bit is implied on the last coefficient
+      const uint64_t v = 1ull | shl64c(ex, z + 1);    // '1', z zeros, '1'
+      bw.append64((uint32_t)v, (uint32_t)(v >> 32), z + 1 + (uint32_t)ex);
+      rr = (R)shr64c((uint64_t)rr, z + 1);
+      p = p1;
+    }
+    if (p < N)
+      bw.append32(0, 1);  // closing (or only) group test
+    pos = p;
+  }
+}
+
+// planes k-1 .. klo of the resident half (first plane kbase), two per vote (k and klo are even)
+template <int N>
 __device__ __forceinline__ void encode_planes_lockstep(ColWriter& bw, uint32_t limit, int kmin, int klo, int kbase,
                                                        LockState& st, const typename PlaneWord<N>::type* sp)
 {
-  using R = typename PlaneWord<N>::type;
   constexpr uint32_t FULL = 0xffffffffu;
   uint32_t pos = st.pos;
   bool done = st.done;
   int k = st.k;
   while (k > klo && __any_sync(FULL, !done)) {
-    k--;
-    done = done || k < kmin || bw.bp >= limit;
-    const R x = sp[(k - kbase) * 32];
-    const uint32_t n = done ? 0u : pos;  // a finished lane appends nothing: zero-length verbatim part, empty T
-    R r, verb;
-    if constexpr (N > 32) {
-      r = shr64c(x, n);
-      verb = x ^ shl64c(r, n);
-    }
-    else {
-      r = shr32c(x, n);
-      verb = x ^ shl32c(r, n);
-    }
-    const R y = done ? (R)0 : r;
-    const bool test = !done && n < N;
-    const uint32_t y32 = (uint32_t)y;
-    const uint32_t c = (uint32_t)__popc(y32);
-    const int msb = 31 - __clz((int)y32);  // -1 when y32 == 0
-    bool slow = false;
-    if constexpr (N > 32)
-      slow = (uint32_t)((uint64_t)y >> 32) != 0 || msb + (int)c + 2 > 32;
-    if (N <= 32 || !__any_sync(FULL, slow)) {
-      uint32_t yp = 0, rem = y32;
-      const uint32_t cmax = __reduce_max_sync(FULL, c);
-      for (uint32_t i = 0; i < cmax; i++) {
-        const uint32_t t = rem & (0u - rem);
-        yp |= t << i;
-        rem ^= t;
-      }
-      const bool has = y32 != 0;
-      const uint32_t top = n + (uint32_t)(msb + 1);    // coefficients settled after this plane
-      const uint32_t last = (has && top == N) ? 1u : 0u;
-      const uint32_t keep = (uint32_t)msb + c - last;   // msb + 1 + c flags and bits, minus the closing flag (and the implied pair)
-      const uint32_t e = (yp * 3u) & mask32(keep);
-      const uint32_t tval = has ? (1u | (e << 1)) : 0u;
-      const uint32_t tlen = has ? keep + 2 - last : (test ? 1u : 0u);
-      pos = has ? top : pos;
-      if constexpr (N > 32)
-        bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
-      else
-        bw.append32((uint32_t)verb, n);
-      bw.append32(tval, tlen);
-    }
-    else {
-      if constexpr (N > 32)
-        bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
-      else
-        bw.append32((uint32_t)verb, n);
-      if (test) {
-        R rr = y;
-        uint32_t p = n;
-        while (rr) {
-          const uint32_t z = ctz_any<R>(rr);
-          const uint32_t p1 = p + z + 1;
-          const uint64_t ex = p1 < N ? 1u : 0u;           // the one-bit is implied on the last coefficient
-          const uint64_t v = 1ull | shl64c(ex, z + 1);    // '1', z zeros, '1'
-          bw.append64((uint32_t)v, (uint32_t)(v >> 32), z + 1 + (uint32_t)ex);
-          rr = (R)shr64c((uint64_t)rr, z + 1);
-          p = p1;
-        }
-        if (p < N)
-          bw.append32(0, 1);  // closing (or only) group test
-        pos = p;
-      }
-    }
+    const typename PlaneWord<N>::type x1 = sp[(k - 1 - kbase) * 32], x2 = sp[(k - 2 - kbase) * 32];
+    encode_plane_lockstep<N>(bw, limit, kmin, k - 1, pos, done, x1);
+    encode_plane_lockstep<N>(bw, limit, kmin, k - 2, pos, done, x2);
+    k -= 2;
   }
   st.pos = pos;
   st.done = done;
@@ -1113,103 +1119,114 @@ struct LockDecodeState {
 };
 
 template <int N>
+__device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, int k, uint32_t& bits, uint32_t& n, int& lowest,
+                                                      bool& done, typename PlaneWord<N>::type* plane)
+{
+  using R = typename PlaneWord<N>::type;
+  constexpr uint32_t FULL = 0xffffffffu;
+  done = done || k < kmin || bits == 0;
+  const uint32_t m = done ? 0u : (n < bits ? n : bits);  // verbatim bits
+  const uint32_t tp = br.bp + m;                         // where T starts
+  R verb;
+  if constexpr (N > 32) {
+    uint32_t lo, hi;
+    br.peek64(br.bp, lo, hi);
+    const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
+    verb = v ^ shl64c(shr64c(v, m), m);
+  }
+  else {
+    const uint32_t v = br.peek32(br.bp);
+    verb = v ^ shl32c(shr32c(v, m), m);
+  }
+  const uint32_t w = br.peek32(tp);
+  const uint32_t left = bits - m;                        // budget at T (m <= bits)
+  const bool test = !done && n < N && left != 0;
+  // parse T: W' = virtual data bit, then the stream
+  const uint32_t wv = (w << 1) | 1u;
+  const uint32_t s = wv & ~(wv << 1);                    // run starts
+  const uint32_t ae = wv + (s & 0x55555555u), ao = wv + (s & 0xaaaaaaaau);
+  const uint32_t term = (ae & ~wv & 0xaaaaaaaau) | (ao & ~wv & 0x55555555u);  // just past each odd-length run
+  const uint32_t tpos = (uint32_t)__ffs((int)term) - 1;  // bits of T (0xffffffff when no end in the window)
+  uint32_t d = ((wv & ~ae & 0x55555554u) | (wv & ~ao & 0xaaaaaaaau)) & mask32(tpos);  // data bits of T, virtual one dropped
+  d = test ? d : 0u;
+  const uint32_t c = (uint32_t)__popc(d);
+  const uint32_t ntop = n + (uint32_t)(31 - __clz((int)d)) - c;  // n + (msb(d) - 2 - (c-1)) + 1: coefficients settled if c > 0
+  // data bits two places down (the virtual bit and the first test), then each moved down by its rank:
+  // y = R0 - (R1 >> 1) - (R2 >> 2) - (R3 >> 3), Rj = the data bits above the lowest j
+  const uint32_t d0 = d >> 2, d1 = d0 & (d0 - 1), d2 = d1 & (d1 - 1), d3 = d2 & (d2 - 1), d4 = d3 & (d3 - 1);
+  bool slow = test && (term == 0 || tpos > left || (c != 0 && ntop > N - 1));
+  uint32_t y = d0 - (d1 >> 1) - (d2 >> 2) - (d3 >> 3);
+  if (__any_sync(FULL, d4 != 0)) {
+    const uint32_t d5 = d4 & (d4 - 1), d6 = d5 & (d5 - 1), d7 = d6 & (d6 - 1), d8 = d7 & (d7 - 1);
+    y -= (d4 >> 4) + (d5 >> 5) + (d6 >> 6) + (d7 >> 7);
+    slow = slow || d8 != 0;
+  }
+  R x;
+  if (!__any_sync(FULL, slow)) {
+    if constexpr (N > 32)
+      x = verb | shl64c((uint64_t)y, n);
+    else
+      x = verb | shl32c(y, n);
+    const uint32_t used = test ? tpos : 0u;
+    bits = left - used;
+    br.bp = tp + used;
+    n = c ? ntop : n;
+  }
+  else {
+    // exact per-item loop (decode.c:96-117) on this plane for every lane
+    x = verb;
+    uint32_t b = left, nn = n, p = tp;
+    if (!done) {
+      while (b && nn < N) {
+        const uint32_t g0 = br.peek32(p);
+        b--;
+        p++;
+        if (!(g0 & 1u))
+          break;
+        const uint32_t room = N - 1 - nn;
+        const uint32_t lim = b < room ? b : room;       // bits the unary scan may read
+        uint32_t taken = 0, g = g0 >> 1, avail = 31;
+        while (taken < lim) {
+          const uint32_t step = lim - taken < avail ? lim - taken : avail;
+          const uint32_t gz = g ? (uint32_t)__ffs((int)g) - 1 : 32u;
+          if (gz < step) {
+            taken += gz + 1;  // gz zeros and the one-bit
+            nn += gz;
+            break;
+          }
+          taken += step;
+          nn += step;
+          g = br.peek32(p + taken);
+          avail = 32;
+        }
+        p += taken;
+        b -= taken;
+        x |= (R)1 << (nn & (8 * sizeof(R) - 1));  // deposited even if the scan ran dry (nn <= N-1)
+        nn++;
+      }
+    }
+    bits = b;
+    br.bp = p;
+    n = nn;
+  }
+  if (!done) {
+    *plane = x;
+    lowest = k;
+  }
+}
+
+template <int N>
 __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, int klo, int kbase, LockDecodeState& st,
                                                        typename PlaneWord<N>::type* sp)
 {
-  using R = typename PlaneWord<N>::type;
   constexpr uint32_t FULL = 0xffffffffu;
   uint32_t bits = st.bits, n = st.n;
   int k = st.k, lowest = st.lowest;
   bool done = st.done;
   while (k > klo && __any_sync(FULL, !done)) {
-    k--;
-    done = done || k < kmin || bits == 0;
-    const uint32_t m = done ? 0u : (n < bits ? n : bits);  // verbatim bits
-    const uint32_t tp = br.bp + m;                         // where T starts
-    R verb;
-    if constexpr (N > 32) {
-      uint32_t lo, hi;
-      br.peek64(br.bp, lo, hi);
-      const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
-      verb = v ^ shl64c(shr64c(v, m), m);
-    }
-    else {
-      const uint32_t v = br.peek32(br.bp);
-      verb = v ^ shl32c(shr32c(v, m), m);
-    }
-    const uint32_t w = br.peek32(tp);
-    const uint32_t left = bits - m;                        // budget at T (m <= bits)
-    const bool test = !done && n < N && left != 0;
-    // parse T: W' = virtual data bit, then the stream
-    const uint32_t wv = (w << 1) | 1u;
-    const uint32_t s = wv & ~(wv << 1);                    // run starts
-    const uint32_t ae = wv + (s & 0x55555555u), ao = wv + (s & 0xaaaaaaaau);
-    const uint32_t term = (ae & ~wv & 0xaaaaaaaau) | (ao & ~wv & 0x55555555u);  // just past each odd-length run
-    const uint32_t tpos = (uint32_t)__ffs((int)term) - 1;  // bits of T (0xffffffff when no end in the window)
-    uint32_t d = ((wv & ~ae & 0x55555554u) | (wv & ~ao & 0xaaaaaaaau)) & mask32(tpos);  // data bits of T, virtual one dropped
-    d = test ? d : 0u;
-    const uint32_t c = (uint32_t)__popc(d);
-    const uint32_t ntop = n + (uint32_t)(31 - __clz((int)d)) - c;  // n + (msb(d) - 2 - (c-1)) + 1: coefficients settled if c > 0
-    const bool slow = test && (term == 0 || tpos > left || (c != 0 && ntop > N - 1));
-    R x;
-    if (!__any_sync(FULL, slow)) {
-      uint32_t y = 0, rem = d;
-      const uint32_t cmax = __reduce_max_sync(FULL, c);
-      for (uint32_t i = 0; i < cmax; i++) {
-        const uint32_t t = rem & (0u - rem);
-        y |= t >> (i + 2);
-        rem ^= t;
-      }
-      if constexpr (N > 32)
-        x = verb | shl64c((uint64_t)y, n);
-      else
-        x = verb | shl32c(y, n);
-      const uint32_t used = test ? tpos : 0u;
-      bits = left - used;
-      br.bp = tp + used;
-      n = c ? ntop : n;
-    }
-    else {
-      // exact per-item loop (decode.c:96-117) on this plane for every lane
-      x = verb;
-      uint32_t b = left, nn = n, p = tp;
-      if (!done) {
-        while (b && nn < N) {
-          const uint32_t g0 = br.peek32(p);
-          b--;
-          p++;
-          if (!(g0 & 1u))
-            break;
-          const uint32_t room = N - 1 - nn;
-          const uint32_t lim = b < room ? b : room;       // bits the unary scan may read
-          uint32_t taken = 0, g = g0 >> 1, avail = 31;
-          while (taken < lim) {
-            const uint32_t step = lim - taken < avail ? lim - taken : avail;
-            const uint32_t gz = g ? (uint32_t)__ffs((int)g) - 1 : 32u;
-            if (gz < step) {
-              taken += gz + 1;  // gz zeros and the one-bit
-              nn += gz;
-              break;
-            }
-            taken += step;
-            nn += step;
-            g = br.peek32(p + taken);
-            avail = 32;
-          }
-          p += taken;
-          b -= taken;
-          x |= (R)1 << (nn & (8 * sizeof(R) - 1));  // deposited even if the scan ran dry (nn <= N-1)
-          nn++;
-        }
-      }
-      bits = b;
-      br.bp = p;
-      n = nn;
-    }
-    if (!done) {
-      sp[(k - kbase) * 32] = x;
-      lowest = k;
-    }
+    decode_plane_lockstep<N>(br, kmin, k - 1, bits, n, lowest, done, sp + (k - 1 - kbase) * 32);
+    decode_plane_lockstep<N>(br, kmin, k - 2, bits, n, lowest, done, sp + (k - 2 - kbase) * 32);
+    k -= 2;
   }
   st.bits = bits;
   st.n = n;
