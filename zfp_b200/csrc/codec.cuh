@@ -249,32 +249,35 @@ __device__ __forceinline__ uint32_t shl32c(uint32_t x, uint32_t n) { uint32_t r;
 struct ColWriter {
   static constexpr bool kStaged = true;
   static constexpr bool kLockstep = true;
-  uint32_t* col;  // word 0 of this lane's column (words are 32 elements apart)
+  uint32_t base;  // shared-space byte address of word 0 of this lane's column (words are 128 bytes apart)
   uint32_t acc;   // bits of the word containing bp that lie below bp
   uint32_t bp;    // bits appended so far
 
-  __device__ __forceinline__ void init(uint32_t* column) { col = column; acc = 0; bp = 0; }
+  __device__ __forceinline__ void init(uint32_t* column)
+  {
+    base = (uint32_t)__cvta_generic_to_shared(column);
+    acc = 0;
+    bp = 0;
+  }
+  __device__ __forceinline__ uint32_t word_addr() const { return base + ((bp & ~31u) << 2); }
   __device__ __forceinline__ void append32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
   {
-    const uint32_t sh = bp & 31;
-    uint32_t* w = col + (bp & ~31u);
+    const uint32_t sh = bp & 31, w = word_addr();
     const uint32_t a0 = acc | (v << sh);
     const uint32_t a1 = __funnelshift_l(v, 0, sh);
-    w[0] = a0;
-    w[32] = a1;
+    asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %2;" ::"r"(w), "r"(a0), "r"(a1) : "memory");
     acc = sh + len < 32 ? a0 : a1;
     bp += len;
   }
   __device__ __forceinline__ void append64(uint32_t lo, uint32_t hi, uint32_t len)  // (hi:lo) < 2^len, len <= 64
   {
-    const uint32_t sh = bp & 31;
-    uint32_t* w = col + (bp & ~31u);
+    const uint32_t sh = bp & 31, w = word_addr();
     const uint32_t a0 = acc | (lo << sh);
     const uint32_t a1 = __funnelshift_l(lo, hi, sh);
     const uint32_t a2 = __funnelshift_l(hi, 0, sh);
-    w[0] = a0;
-    w[32] = a1;
-    w[64] = a2;
+    asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %2;\n\tst.shared.u32 [%0+256], %3;" ::"r"(w), "r"(a0), "r"(a1),
+                 "r"(a2)
+                 : "memory");
     const uint32_t t = sh + len;  // <= 95
     acc = t < 32 ? a0 : (t < 64 ? a1 : a2);
     bp += len;
@@ -286,7 +289,7 @@ struct ColWriter {
   __device__ __forceinline__ void finish(uint32_t total_words)
   {
     for (uint32_t w = (bp >> 5) + 1; w < total_words; w++)
-      col[w * 32] = 0;
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (w << 7)), "r"(0u) : "memory");
   }
 };
 
@@ -431,19 +434,26 @@ struct StageReader {
 struct ColReader {
   static constexpr bool kStaged = true;
   static constexpr bool kLockstep = true;
-  const uint32_t* col;
-  uint32_t bp;  // bits consumed so far
+  uint32_t base;  // shared-space byte address of word 0 of this lane's column (words are 128 bytes apart)
+  uint32_t bp;    // bits consumed so far
 
-  __device__ __forceinline__ void init(const uint32_t* column) { col = column; bp = 0; }
+  __device__ __forceinline__ void init(const uint32_t* column)
+  {
+    base = (uint32_t)__cvta_generic_to_shared(column);
+    bp = 0;
+  }
   __device__ __forceinline__ uint32_t peek32(uint32_t pos) const  // the 32 bits starting at bit `pos`
   {
-    const uint32_t* w = col + (pos & ~31u);
-    return __funnelshift_r(w[0], w[32], pos);  // shift amount is taken modulo 32
+    uint32_t w0, w1;
+    asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+128];" : "=r"(w0), "=r"(w1) : "r"(base + ((pos & ~31u) << 2)));
+    return __funnelshift_r(w0, w1, pos);  // shift amount is taken modulo 32
   }
   __device__ __forceinline__ void peek64(uint32_t pos, uint32_t& lo, uint32_t& hi) const
   {
-    const uint32_t* w = col + (pos & ~31u);
-    const uint32_t w0 = w[0], w1 = w[32], w2 = w[64];
+    uint32_t w0, w1, w2;
+    asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+128];\n\tld.shared.u32 %2, [%3+256];"
+                 : "=r"(w0), "=r"(w1), "=r"(w2)
+                 : "r"(base + ((pos & ~31u) << 2)));
     lo = __funnelshift_r(w0, w1, pos);
     hi = __funnelshift_r(w1, w2, pos);
   }
@@ -1118,26 +1128,51 @@ struct LockDecodeState {
   bool done;
 };
 
+// What is left to do for a parsed plane: fetch its m verbatim bits (they start at bp0), merge the
+// newly significant bits and store the plane word.  Deferred by one plane so that this independent
+// work sits in the same basic block as the next plane's dependent parse chain.
 template <int N>
-__device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, int k, uint32_t& bits, uint32_t& n, int& lowest,
-                                                      bool& done, typename PlaneWord<N>::type* plane)
+struct PlaneRec {
+  typename PlaneWord<N>::type ybits;  // bits decoded from the group-tested part, at their coefficient positions
+  uint32_t bp0, m;
+  typename PlaneWord<N>::type* dst;
+  bool store;
+};
+
+template <int N>
+__device__ __forceinline__ void finish_plane(const ColReader& br, const PlaneRec<N>& rec)
 {
   using R = typename PlaneWord<N>::type;
-  constexpr uint32_t FULL = 0xffffffffu;
-  done = done || k < kmin || bits == 0;
-  const uint32_t m = done ? 0u : (n < bits ? n : bits);  // verbatim bits
-  const uint32_t tp = br.bp + m;                         // where T starts
   R verb;
   if constexpr (N > 32) {
     uint32_t lo, hi;
-    br.peek64(br.bp, lo, hi);
+    br.peek64(rec.bp0, lo, hi);
     const uint64_t v = (uint64_t)lo | ((uint64_t)hi << 32);
-    verb = v ^ shl64c(shr64c(v, m), m);
+    verb = v ^ shl64c(shr64c(v, rec.m), rec.m);
   }
   else {
-    const uint32_t v = br.peek32(br.bp);
-    verb = v ^ shl32c(shr32c(v, m), m);
+    const uint32_t v = br.peek32(rec.bp0);
+    verb = v ^ shl32c(shr32c(v, rec.m), rec.m);
   }
+  if (rec.store)
+    *rec.dst = verb | rec.ybits;
+}
+
+template <int N>
+__device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, int k, uint32_t& bits, uint32_t& n, int& lowest,
+                                                      bool& done, typename PlaneWord<N>::type* plane, PlaneRec<N>& rec)
+{
+  using R = typename PlaneWord<N>::type;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const PlaneRec<N> prev = rec;
+  done = done || k < kmin || bits == 0;
+  const uint32_t m = done ? 0u : (n < bits ? n : bits);  // verbatim bits
+  const uint32_t tp = br.bp + m;                         // where T starts
+  rec.bp0 = br.bp;
+  rec.m = m;
+  rec.dst = plane;
+  rec.store = !done;
+  lowest = done ? lowest : k;
   const uint32_t w = br.peek32(tp);
   const uint32_t left = bits - m;                        // budget at T (m <= bits)
   const bool test = !done && n < N && left != 0;
@@ -1156,17 +1191,17 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   const uint32_t d0 = d >> 2, d1 = d0 & (d0 - 1), d2 = d1 & (d1 - 1), d3 = d2 & (d2 - 1), d4 = d3 & (d3 - 1);
   bool slow = test && (term == 0 || tpos > left || (c != 0 && ntop > N - 1));
   uint32_t y = d0 - (d1 >> 1) - (d2 >> 2) - (d3 >> 3);
+  finish_plane<N>(br, prev);  // the previous plane's leftover work: independent of everything above
   if (__any_sync(FULL, d4 != 0)) {
     const uint32_t d5 = d4 & (d4 - 1), d6 = d5 & (d5 - 1), d7 = d6 & (d6 - 1), d8 = d7 & (d7 - 1);
     y -= (d4 >> 4) + (d5 >> 5) + (d6 >> 6) + (d7 >> 7);
     slow = slow || d8 != 0;
   }
-  R x;
   if (!__any_sync(FULL, slow)) {
     if constexpr (N > 32)
-      x = verb | shl64c((uint64_t)y, n);
+      rec.ybits = shl64c((uint64_t)y, n);
     else
-      x = verb | shl32c(y, n);
+      rec.ybits = shl32c(y, n);
     const uint32_t used = test ? tpos : 0u;
     bits = left - used;
     br.bp = tp + used;
@@ -1174,7 +1209,7 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   }
   else {
     // exact per-item loop (decode.c:96-117) on this plane for every lane
-    x = verb;
+    R x = 0;
     uint32_t b = left, nn = n, p = tp;
     if (!done) {
       while (b && nn < N) {
@@ -1205,13 +1240,10 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
         nn++;
       }
     }
+    rec.ybits = x;
     bits = b;
     br.bp = p;
     n = nn;
-  }
-  if (!done) {
-    *plane = x;
-    lowest = k;
   }
 }
 
@@ -1223,11 +1255,13 @@ __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, 
   uint32_t bits = st.bits, n = st.n;
   int k = st.k, lowest = st.lowest;
   bool done = st.done;
+  PlaneRec<N> rec = { 0, 0, 0, sp, false };
   while (k > klo && __any_sync(FULL, !done)) {
-    decode_plane_lockstep<N>(br, kmin, k - 1, bits, n, lowest, done, sp + (k - 1 - kbase) * 32);
-    decode_plane_lockstep<N>(br, kmin, k - 2, bits, n, lowest, done, sp + (k - 2 - kbase) * 32);
+    decode_plane_lockstep<N>(br, kmin, k - 1, bits, n, lowest, done, sp + (k - 1 - kbase) * 32, rec);
+    decode_plane_lockstep<N>(br, kmin, k - 2, bits, n, lowest, done, sp + (k - 2 - kbase) * 32, rec);
     k -= 2;
   }
+  finish_plane<N>(br, rec);
   st.bits = bits;
   st.n = n;
   st.k = k;
@@ -1260,18 +1294,31 @@ __device__ __forceinline__ int block_emax(const typename TR::Scalar (&v)[N])
   using U = typename TR::UInt;
   const U absmask = ~(U)0 >> 1, infbits = (U)((1u << TR::EBITS) - 1) << TR::MANT;
   if constexpr (!EXACT && sizeof(U) == 8) {
-    uint32_t top = 0, any_hi = 0, any_lo = 0;
+    // The high words are sign-magnitude: as signed integers the maximum is the largest positive
+    // value (or, with no positive value, the negative one of largest magnitude), as unsigned
+    // integers it is the negative value of largest magnitude (or the largest positive one); the
+    // larger of the two magnitudes is the block maximum.  Two 3-input max chains, no masking.
+    int32_t smax = (int32_t)0x80000000;
+    uint32_t umax = 0;
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-      const uint64_t b = FpBits<typename TR::Scalar>::bits(v[i]);
-      const uint32_t hi = (uint32_t)(b >> 32) & 0x7fffffffu;
-      top = hi > top ? hi : top;
-      any_hi |= hi;
-      any_lo |= (uint32_t)b;
+    for (int i = 0; i < N; i += 2) {
+      const uint32_t h0 = (uint32_t)(FpBits<typename TR::Scalar>::bits(v[i]) >> 32);
+      const uint32_t h1 = (uint32_t)(FpBits<typename TR::Scalar>::bits(v[(i + 1) % N]) >> 32);
+      smax = __vimax3_s32(smax, (int32_t)h0, (int32_t)h1);
+      umax = __vimax3_u32(umax, h0, h1);
     }
+    const uint32_t a = (uint32_t)smax & 0x7fffffffu, b = umax & 0x7fffffffu;
+    const uint32_t top = a > b ? a : b;
     const int E = (int)(top >> 20);
     if (E) return E - TR::EBIAS + 1;
-    return (any_hi | any_lo) ? 1 - TR::EBIAS : -TR::EBIAS;
+    // subnormal or zero block (rare): look at all the bits
+    uint32_t any = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const uint64_t w = FpBits<typename TR::Scalar>::bits(v[i]);
+      any |= ((uint32_t)(w >> 32) & 0x7fffffffu) | (uint32_t)w;
+    }
+    return any ? 1 - TR::EBIAS : -TR::EBIAS;
   }
   U m = 0;
 #pragma unroll
@@ -1317,6 +1364,13 @@ __device__ __forceinline__ void cast_fwd(typename TR::Int (&q)[N], const typenam
   const int se = TR::P - 2 - emax;
   const Scalar s = pow2<Scalar>(se);
   const bool overflow = se > (TR::P == 32 ? 127 : 1023);
+  // tiny block maxima (infinite scale) are rare: whole warps skip the per-value selects
+  if (!__any_sync(__activemask(), overflow)) {
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      q[i] = cvt_rz(s * v[i]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < N; i++) {
     Int r = cvt_rz(s * v[i]);
@@ -1472,7 +1526,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     LockState st = { 0, P, !coded };
     if constexpr (P == 64) {
       to_planes_half<1, UInt, N>(u, sp);
-      encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+        encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
       if (__any_sync(0xffffffffu, !st.done)) {
         to_planes_half<0, UInt, N>(u, sp);
         encode_planes_lockstep<N>(bw, start + budget, kmin, 0, 0, st, sp);
@@ -1570,6 +1624,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
       u[i] = 0;
     if constexpr (P == 64) {
       decode_planes_lockstep<N>(br, kmin, 32, 32, st, sp);
+      __syncthreads();  // the warps of the CTA enter the long straight-line tail together (shared instruction fetch)
       from_planes_half<1, UInt, N>(u, sp, st.lowest);
       if (__any_sync(0xffffffffu, !st.done)) {
         decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);

@@ -103,7 +103,7 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
 {
   constexpr int N = 1 << (2 * DIMS);
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
-  const size_t smem = (size_t)(kThreads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
+  const size_t smem = (size_t)(DecCfg<TYPE>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4);
   static size_t allowed = 0;
   if (smem > 48 * 1024 && smem > allowed) {
@@ -111,8 +111,8 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
     if (e != cudaSuccess) return e;
     allowed = smem;
   }
-  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
-  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+  const uint64_t ctas = (a.g.nblocks + DecCfg<TYPE>::threads - 1) / DecCfg<TYPE>::threads;
+  kernel<<<(unsigned)ctas, DecCfg<TYPE>::threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<const uint64_t*>(a.in), a.start_bit);
   return cudaGetLastError();
 }
