@@ -100,6 +100,35 @@ def test_device_vs_oracle_analytic(zb, port, dtype, shape):
             assert np.max(np.abs(back.astype(np.float64) - a.astype(np.float64))) <= mode["accuracy"]
 
 
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (36, 40, 44)), (np.float32, (40, 36, 44)), (np.int64, (33, 32, 36)),
+                                         (np.float64, (70, 66)), (np.int32, (1000,))])
+def test_long_blocks_and_noisy_planes(zb, port, dtype, shape):
+    """Noise and mixed noise/smooth/zero fields at high precision: blocks far longer than the
+    shared-memory staging window of the variable-rate kernels (drain / restage), bit planes with
+    many runs (the lockstep coders' per-item fallback), warps whose lanes finish at very
+    different planes, and fixed rates where the budget runs out inside a group test."""
+    import torch
+    noise = make_field(shape, dtype, 11, "noise")
+    smooth = make_field(shape, dtype, 12, "smooth")
+    mixed = noise.copy()
+    flat = mixed.reshape(-1)
+    flat[: flat.size // 3] = smooth.reshape(-1)[: flat.size // 3]   # smooth part
+    flat[flat.size // 3: flat.size // 2] = 0                          # zero blocks
+    modes = [{"precision": 48}, {"precision": 30}, {"rate": 3}, {"rate": 24}, {"rate": 48}, {"expert": (64, 1900, 40, -1074)}]
+    if np.dtype(dtype).kind == "f":
+        modes += [{"accuracy": 1e-12}, {"accuracy": 1e-3}, {"expert": (1, 16000, 64, -1074)}]
+    for a in (noise, mixed):
+        x = torch.from_numpy(a).cuda()
+        for mode in modes:
+            c = zb.compress(x, **mode)
+            want = port.compress(a, **mode)
+            got = c.to_numpy()
+            assert got.nbytes == want.nbytes, (mode, got.nbytes, want.nbytes)
+            assert got.tobytes() == want.tobytes(), mode
+            back = zb.decompress(c).cpu().numpy()
+            assert back.tobytes() == port.decompress(want, a.shape, a.dtype, **mode).tobytes(), mode
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_strides_and_stream_offsets(zb, port, dtype):
     """Negative, gapped and permuted strides; payload starting mid-word after a header."""

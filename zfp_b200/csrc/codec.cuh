@@ -126,112 +126,12 @@ struct BitWriter {
   }
 };
 
-// ------------------------------------------------------------------------------------------------
-// staged writer (fast fixed-rate path): the block's bits are assembled as 32-bit words in a
-// lane-private shared-memory column ([word][lane], bank = lane: conflict free whatever word each
-// lane is at) and copied out with wide stores by the kernel.  No per-append budget clamps: the
-// coder may overshoot by up to a plane; finish() drops everything at or beyond the block's bit
-// budget (word aligned in this mode), which is exactly the reference's truncation.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t mask32(uint32_t len)  // low `len` bits set, 0 <= len <= 32
+__device__ __forceinline__ uint32_t mask32(uint32_t len)  // low `len` bits set, 0 <= len <= 32 (larger values clamp)
 {
   uint32_t r;
   asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(len));
   return r;
 }
-
-constexpr uint32_t kPlaneMaxWords = 8;  // a plane appends < 200 bits: 7 words, plus one being filled
-
-struct StageWriter {
-  static constexpr bool kStaged = true;
-  uint32_t* p;   // next staging word of this lane (stride 32 words)
-  uint32_t* p0;
-  uint32_t lo, hi, fill;
-  // variable-rate use: the column holds `cap` words; when it runs low the complete words are
-  // drained to the block's slot in global memory (gdst) and `base` counts the drained bits
-  uint32_t* gdst;
-  uint32_t base, cap;
-
-  __device__ __forceinline__ void init(uint32_t* column, uint32_t* slot = nullptr, uint32_t capacity_words = 0)
-  {
-    p = p0 = column;
-    lo = hi = 0;
-    fill = 0;
-    gdst = slot;
-    base = 0;
-    cap = capacity_words;
-  }
-  // variable rate only; call where at most kPlaneMaxWords more words may be appended before the
-  // next call (plane boundaries)
-  __device__ __forceinline__ void drain_if_low()
-  {
-    if (gdst && (uint32_t)(p - p0) > (cap - kPlaneMaxWords) * 32)
-      drain();
-  }
-  __device__ __forceinline__ void drain()
-  {
-    const uint32_t n = (uint32_t)(p - p0) >> 5;
-    for (uint32_t j = 0; j < n; j++)
-      gdst[j] = p0[j * 32];
-    gdst += n;
-    base += n * 32;
-    p = p0;
-  }
-  __device__ __forceinline__ void put32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
-  {
-    lo |= v << fill;
-    hi = __funnelshift_l(v, 0, fill);  // the part of v that does not fit the current word
-    fill += len;                       // <= 63
-    const uint32_t full = fill & 32;   // 32 when the current word is complete, else 0
-    if (full)
-      *p = lo;
-    p += full;                         // words of a lane are 32 elements apart
-    lo = full ? hi : lo;
-    fill &= 31;
-  }
-  __device__ __forceinline__ void put(uint64_t v, uint32_t len)  // len <= 64
-  {
-    if (len <= 32)
-      put32((uint32_t)v, len);
-    else {
-      put32((uint32_t)v, 32);
-      put32((uint32_t)(v >> 32), len - 32);
-    }
-  }
-  __device__ __forceinline__ void skip(uint32_t zeros)
-  {
-    fill += zeros;
-    while (fill >= 32) {
-      *p = lo;
-      p += 32;
-      lo = 0;
-      fill -= 32;
-      if (gdst && (uint32_t)(p - p0) >= cap * 32)
-        drain();
-    }
-  }
-  __device__ __forceinline__ void pad(uint32_t zeros) { skip(zeros); }
-  __device__ __forceinline__ uint32_t tell() const { return base + (uint32_t)(p - p0) + fill; }  // (p-p0)/32 words * 32 bits
-  // variable rate: flush everything to the slot
-  __device__ __forceinline__ void finish_slot()
-  {
-    if (fill) {
-      *p = lo;
-      p += 32;
-    }
-    drain();
-  }
-  // close the block at exactly total_words 32-bit words: flush, zero-fill, ignore overshoot
-  __device__ __forceinline__ void finish(uint32_t total_words)
-  {
-    if (fill) {
-      *p = lo;
-      p += 32;
-    }
-    for (uint32_t* q = p; q < p0 + 32 * total_words; q += 32)
-      *q = 0;
-  }
-};
 
 // PTX shifts clamp the shift amount at the register width (a shift by >= width gives 0), which is
 // exactly what the coder wants at n == N; C++ shifts leave that case undefined.
@@ -240,8 +140,9 @@ __device__ __forceinline__ uint64_t shl64c(uint64_t x, uint32_t n) { uint64_t r;
 __device__ __forceinline__ uint32_t shr32c(uint32_t x, uint32_t n) { uint32_t r; asm("shr.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
 __device__ __forceinline__ uint32_t shl32c(uint32_t x, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(n)); return r; }
 
-// Column writer (plane-lockstep fixed-rate path): same lane-private [word][lane] column as
-// StageWriter, addressed by bit position.  An append ORs the value into the partial word kept in
+// Column writer (plane-lockstep coder): the block's bits are assembled as 32-bit words in a
+// lane-private shared-memory column ([word][lane], bank = lane: conflict free whatever word each
+// lane is at), addressed by bit position.  An append ORs the value into the partial word kept in
 // `acc` and stores every word the value can touch UNCONDITIONALLY (a later append rewrites the
 // partial word with more bits in it): no predicates, no flush test, and the word holding `bp` is
 // always current in shared memory.  Words beyond it hold zeros or were never written; finish()
@@ -251,13 +152,43 @@ struct ColWriter {
   static constexpr bool kLockstep = true;
   uint32_t base;  // shared-space byte address of word 0 of this lane's column (words are 128 bytes apart)
   uint32_t acc;   // bits of the word containing bp that lie below bp
-  uint32_t bp;    // bits appended so far
+  uint32_t bp;    // bits appended so far (variable rate: since the last drain)
+  // variable rate: the column is a window of `cap` words; when it runs low its complete words
+  // leave for the block's slot in global memory (gdst) and `drained` counts their bits
+  uint32_t* gdst;
+  uint32_t drained, cap;
 
-  __device__ __forceinline__ void init(uint32_t* column)
+  __device__ __forceinline__ void init(uint32_t* column, uint32_t* slot = nullptr, uint32_t capacity_words = 0)
   {
     base = (uint32_t)__cvta_generic_to_shared(column);
     acc = 0;
     bp = 0;
+    gdst = slot;
+    drained = 0;
+    cap = capacity_words;
+  }
+  // call at plane boundaries: a plane appends < 200 bits and an append stores two words ahead
+  __device__ __forceinline__ void drain_if_low()
+  {
+    if (gdst && bp > (cap - 10) * 32)
+      drain(bp >> 5);
+  }
+  __device__ __forceinline__ void drain(uint32_t nwords)
+  {
+    for (uint32_t j = 0; j < nwords; j++) {
+      uint32_t v;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (j << 7)));
+      gdst[j] = v;
+    }
+    gdst += nwords;
+    drained += nwords * 32;
+    bp &= 31;  // the partial word lives in acc; the next append rewrites column word 0 from it
+  }
+  // variable rate: everything (including the partial word) to the slot
+  __device__ __forceinline__ void finish_slot()
+  {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(word_addr()), "r"(acc) : "memory");
+    drain((bp + 31) >> 5);
   }
   __device__ __forceinline__ uint32_t word_addr() const { return base + ((bp & ~31u) << 2); }
   __device__ __forceinline__ void append32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
@@ -283,8 +214,18 @@ struct ColWriter {
     bp += len;
   }
   __device__ __forceinline__ void put(uint64_t v, uint32_t len) { append64((uint32_t)v, (uint32_t)(v >> 32), len); }
-  __device__ __forceinline__ void pad(uint32_t) {}  // finish() zero-fills
-  __device__ __forceinline__ uint32_t tell() const { return bp; }
+  __device__ __forceinline__ void pad(uint32_t zeros)  // fixed rate: finish() zero-fills instead
+  {
+    if (gdst) {
+      while (zeros) {
+        const uint32_t step = zeros < 32 ? zeros : 32;
+        append32(0, step);
+        zeros -= step;
+        drain_if_low();
+      }
+    }
+  }
+  __device__ __forceinline__ uint32_t tell() const { return drained + bp; }
   // close the block at exactly total_words 32-bit words: zero-fill; overshoot is simply not copied
   __device__ __forceinline__ void finish(uint32_t total_words)
   {
@@ -342,92 +283,6 @@ struct BitReader {
   }
 };
 
-// staged reader (fast fixed-rate path): the block's words were copied to a lane-private
-// shared-memory column ([word][lane]); a 64-bit window holds more than 32 valid bits at all
-// times so any read of <= 32 bits needs no refill check before it, only after.
-struct StageReader {
-  static constexpr bool kStaged = true;
-  const uint32_t* p;  // next word to fetch (stride 32 words)
-  uint32_t lo, hi;    // window, LSB first
-  uint32_t avail;     // valid bits in the window, 33..64 between calls
-  // variable-rate use: the column holds a `cap`-word window of the block's words, which start at
-  // gsrc (32-bit words) and number `left` from there; restage_if_low() slides the window
-  uint32_t* col;
-  const uint32_t* gsrc;
-  uint32_t left, cap;
-
-  __device__ __forceinline__ void init(const uint32_t* column)
-  {
-    lo = column[0];
-    hi = column[32];
-    p = column + 64;
-    avail = 64;
-    gsrc = nullptr;
-  }
-  // variable rate: (re)fill the column from global memory and position the window `phase` bits in
-  __device__ __forceinline__ void stage(uint32_t phase)
-  {
-    const uint32_t n = left < cap ? left : cap;
-    for (uint32_t j = 0; j < cap; j++)
-      col[j * 32] = j < n ? __ldg(gsrc + j) : 0u;
-    lo = col[0];
-    hi = col[32];
-    p = col + 64;
-    avail = 64;
-    skip32(phase);
-  }
-  __device__ __forceinline__ void init_var(uint32_t* column, uint32_t capacity_words, const uint32_t* src, uint32_t words,
-                                           uint32_t phase)
-  {
-    col = column;
-    cap = capacity_words;
-    gsrc = src;
-    left = words;
-    stage(phase);
-  }
-  // call at plane boundaries: a plane reads < 200 bits, the window looks two words ahead and the
-  // branch-free refill peeks one more
-  __device__ __forceinline__ void restage_if_low()
-  {
-    if (gsrc && (uint32_t)(p - col) > (cap - kPlaneMaxWords - 3) * 32) {
-      const uint32_t consumed = (uint32_t)(p - col) - avail;  // bits, relative to the column start
-      gsrc += consumed >> 5;
-      left = left > (consumed >> 5) ? left - (consumed >> 5) : 0;
-      stage(consumed & 31);
-    }
-  }
-  __device__ __forceinline__ uint32_t peek32() const { return lo; }
-  __device__ __forceinline__ void skip32(uint32_t len)  // len <= 32
-  {
-    lo = __funnelshift_rc(lo, hi, len);
-    hi = __funnelshift_rc(hi, 0, len);
-    avail -= len;
-    // branch-free refill: the next word is always fetched (a lane-private shared-memory load) and
-    // merged at bit position `avail` only when the window has dropped to 32 valid bits or fewer
-    const uint32_t w = *p;
-    const bool need = avail <= 32;
-    const uint32_t add_lo = __funnelshift_lc(0, w, avail);  // w << avail, 0 when avail == 32
-    const uint32_t add_hi = __funnelshift_lc(w, 0, avail);  // w >> (32 - avail), w when avail == 32
-    lo |= need ? add_lo : 0u;
-    hi |= need ? add_hi : 0u;
-    avail += need ? 32u : 0u;
-    p += need ? 32 : 0;
-  }
-  __device__ __forceinline__ uint32_t get32(uint32_t len)  // len <= 32
-  {
-    const uint32_t v = lo & mask32(len);
-    skip32(len);
-    return v;
-  }
-  __device__ __forceinline__ uint64_t get(uint32_t len)  // len <= 64
-  {
-    if (len <= 32)
-      return get32(len);
-    const uint32_t a = get32(32);
-    return (uint64_t)a | ((uint64_t)get32(len - 32) << 32);
-  }
-};
-
 // Column reader (plane-lockstep fixed-rate path): the block's words sit in a lane-private
 // [word][lane] column followed by zero words; reads are by bit position straight from shared memory
 // (no register window to maintain), so all loads of a plane are issued together.
@@ -435,12 +290,44 @@ struct ColReader {
   static constexpr bool kStaged = true;
   static constexpr bool kLockstep = true;
   uint32_t base;  // shared-space byte address of word 0 of this lane's column (words are 128 bytes apart)
-  uint32_t bp;    // bits consumed so far
+  uint32_t bp;    // read position in the column, bits
+  // variable rate: the column holds a `cap`-word window of the block's words, which start at gsrc
+  // (32-bit words) and number `left` from there; restage() slides the window
+  const uint32_t* gsrc;
+  uint32_t left, cap;
 
   __device__ __forceinline__ void init(const uint32_t* column)
   {
     base = (uint32_t)__cvta_generic_to_shared(column);
     bp = 0;
+    gsrc = nullptr;
+    left = cap = 0;
+  }
+  __device__ __forceinline__ void stage()
+  {
+    const uint32_t n = left < cap ? left : cap;
+    for (uint32_t j = 0; j < cap; j++)
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (j << 7)), "r"(j < n ? __ldg(gsrc + j) : 0u) : "memory");
+  }
+  __device__ __forceinline__ void init_var(const uint32_t* column, uint32_t capacity_words, const uint32_t* src, uint32_t words,
+                                           uint32_t phase)
+  {
+    base = (uint32_t)__cvta_generic_to_shared(column);
+    cap = capacity_words;
+    gsrc = src;
+    left = words;
+    stage();
+    bp = phase;
+  }
+  // checked every two planes: each reads < 200 bits past its start and every read looks up to three words ahead
+  __device__ __forceinline__ bool needs_restage() const { return gsrc && bp > (cap - 16) * 32; }
+  __device__ __forceinline__ void restage()
+  {
+    const uint32_t adv = bp >> 5;
+    gsrc += adv;
+    left = left > adv ? left - adv : 0;
+    stage();
+    bp &= 31;
   }
   __device__ __forceinline__ uint32_t peek32(uint32_t pos) const  // the 32 bits starting at bit `pos`
   {
@@ -740,98 +627,9 @@ __device__ __forceinline__ uint32_t encode_planes(Writer& bw, uint32_t budget, u
   return budget - bits;
 }
 
-// Fast variant for the staged writer.  Uses two facts about the reference coder (encode.c:91-132):
-// the number n of coefficients coded verbatim in plane k is 1 + the highest coefficient index set
-// in any plane above k, and a one-bit that falls on the last coefficient is implied.
-//
-// The loop is flattened so that divergence between the 32 blocks of a warp costs little: every
-// iteration does the same work for every lane - (if the lane starts a new plane) fetch it and
-// append its n verbatim bits, then append ONE group-tested item: either the closing '0' test of a
-// plane without new coefficients, or one run ('1', z zeros, '1'; the last coefficient's one-bit is
-// implied), with the closing '0' folded in when it was the plane's last run.  Lanes whose planes
-// have several runs simply spend more iterations.  The bit budget is enforced by truncation in
-// StageWriter::finish().
 template <class T> __device__ __forceinline__ uint32_t ctz_any(T x);
 template <> __device__ __forceinline__ uint32_t ctz_any<uint32_t>(uint32_t x) { return (uint32_t)__ffs((int)x) - 1; }
 template <> __device__ __forceinline__ uint32_t ctz_any<uint64_t>(uint64_t x) { return ctz64(x); }
-
-struct EncodeState {
-  uint64_t r;     // group-tested bits of the current plane still to code (bit 0 = coefficient pos)
-  uint32_t pos;   // coefficients settled so far: carries over as the next plane's verbatim count n
-  int k;          // current plane (starts at P)
-  bool done;      // budget exhausted or all planes coded
-};
-
-// Codes planes down to klo (inclusive) from the resident half whose first plane is kbase; returns
-// with st.done set when the block is finished, or cleared when it needs planes below klo.
-// TIGHT: code all runs of a plane in an inner loop instead of one per (warp-wide) iteration - better
-// when planes are noisy and have many runs (reversible mode's residuals), worse for smooth data.
-template <int N, bool TIGHT>
-__device__ __forceinline__ void encode_planes_staged(StageWriter& bw, uint32_t start, uint32_t budget, int kmin, int klo,
-                                                     int kbase, EncodeState& st, const typename PlaneWord<N>::type* sp)
-{
-  using R = typename PlaneWord<N>::type;  // 32-bit arithmetic suffices for blocks of <= 32 values
-  constexpr uint32_t RB = 8 * sizeof(R);
-  R r = (R)st.r;
-  uint32_t pos = st.pos;
-  int k = st.k;
-  bool done = false;
-  for (;;) {
-    uint32_t vlo = 0, vhi = 0, l1 = 0, l2 = 0;
-    bool fresh = false;
-    if (!r) {
-      // previous plane complete: fetch the next one
-      if (k - 1 < kmin || bw.tell() - start >= budget) {
-        done = true;
-        break;
-      }
-      if (k - 1 < klo)
-        break;
-      k--;
-      bw.drain_if_low();
-      const R x = sp[(k - kbase) * 32];
-      const uint32_t n = pos;  // <= N
-      l1 = n < 32 ? n : 32;
-      vlo = (uint32_t)x & mask32(l1);
-      if (N > 32) {
-        l2 = n - l1;
-        vhi = (uint32_t)((uint64_t)x >> 32) & mask32(l2);
-      }
-      r = n < RB ? (R)(x >> n) : (R)0;
-      fresh = true;
-    }
-    bw.put32(vlo, l1);
-    if (N > 32)
-      bw.put32(vhi, l2);
-    do {
-      // one group-tested item with a single append: a run ('1', z zeros, '1' - implied on the last
-      // coefficient - plus the plane's closing '0' test when it was the last run), or the lone '0'
-      // test of a plane without new coefficients
-      const bool run = r != 0;
-      const uint32_t z = run ? ctz_any<R>(r) : 0u;  // zeros before the next one-bit
-      const uint32_t pos1 = run ? pos + z + 1 : pos;
-      const R r1 = (run && z < RB - 1) ? (R)(r >> (z + 1)) : (R)0;
-      const uint32_t explicit_one = pos1 < N ? 1u : 0u;
-      const uint32_t closing = (run && !r1 && pos1 < N) ? 1u : 0u;
-      if (run && z >= 29) {
-        bw.put32(1, 1);
-        bw.skip(z);
-        bw.put32(explicit_one, explicit_one + closing);
-      }
-      else {
-        const uint32_t v = run ? (1u | (explicit_one << (z + 1))) : 0u;
-        const uint32_t len = run ? z + 1 + explicit_one + closing : ((fresh && pos < N) ? 1u : 0u);
-        bw.put32(v, len);
-      }
-      pos = pos1;
-      r = r1;
-    } while (TIGHT && r);
-  }
-  st.r = r;
-  st.pos = pos;
-  st.k = k;
-  st.done = done;
-}
 
 // Plane-lockstep coder for the column writer.  All 32 lanes walk the planes together (k is warp
 // uniform); per plane a lane appends the n verbatim bits in one go, then the whole group-tested
@@ -853,7 +651,8 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
 {
   using R = typename PlaneWord<N>::type;
   constexpr uint32_t FULL = 0xffffffffu;
-  done = done || k < kmin || bw.bp >= limit;
+  bw.drain_if_low();
+  done = done || k < kmin || bw.tell() >= limit;
   const uint32_t n = done ? 0u : pos;  // a finished lane appends nothing: zero-length verbatim part, empty T
   R r, verb;
   if constexpr (N > 32) {
@@ -967,147 +766,6 @@ __device__ __forceinline__ uint32_t decode_planes(BitReader& br, uint32_t budget
   }
   kstop = k + 1;
   return budget - bits;
-}
-
-// Group-tested part of one plane with exact budget accounting, one bit at a time (the reference's
-// loop, decode.c:96-117, including its deposit-on-exhaustion rule).  Used where the budget may bind.
-template <int N, class Reader>
-__device__ __forceinline__ void decode_group_exact(Reader& br, uint32_t& bits, uint32_t& n, uint64_t& x)
-{
-  while (bits && n < N) {
-    bits--;
-    if (!br.get32(1))
-      break;
-    while (bits && n < N - 1) {
-      bits--;
-      if (br.get32(1))
-        break;
-      n++;
-    }
-    x |= 1ull << n;
-    n++;
-  }
-}
-
-// Fast variant for the staged reader: the mirror image of encode_planes_staged, flattened the same
-// way (per iteration: optionally start a plane by reading its verbatim bits, then decode one
-// group-tested item).  Budget accounting is exact at every step, including the reference's
-// deposit-on-exhaustion rule (decode.c:103-111): a run is limited to min(bits left, N-1-n) zeros
-// and the one-bit is deposited where the scan stopped.
-struct DecodeState {
-  uint64_t x;     // plane being assembled
-  uint32_t bits;  // budget left
-  uint32_t n;     // coefficients significant so far
-  int k;          // current plane (starts at P)
-  int lowest;     // lowest plane stored so far (P when none)
-  bool open;      // a plane is in progress (its next item starts with a group test)
-  bool done;      // budget exhausted or all planes decoded
-};
-
-template <int N, bool TIGHT>
-__device__ __forceinline__ void decode_planes_staged(StageReader& br, int kmin, int klo, int kbase, DecodeState& st,
-                                                     typename PlaneWord<N>::type* sp)
-{
-  uint32_t bits = st.bits, n = st.n;
-  uint64_t x = st.x;
-  bool open = st.open, finished = false;
-  int k = st.k, lowest = st.lowest;
-  for (;;) {
-    const bool start = !open;
-    if (start) {
-      if (!bits || k - 1 < kmin) {
-        finished = true;
-        break;
-      }
-      if (k - 1 < klo)
-        break;
-      k--;
-      br.restage_if_low();
-    }
-    {
-      // verbatim bits of a plane that starts now (zero-length reads otherwise: uniform code)
-      const uint32_t m = start ? (n < bits ? n : bits) : 0u;
-      const uint32_t l1 = m < 32 ? m : 32;
-      const uint32_t v1 = br.get32(l1);
-      uint32_t v2 = 0;
-      if (N > 32)
-        v2 = br.get32(m - l1);
-      x = start ? ((uint64_t)v1 | ((uint64_t)v2 << 32)) : x;
-      bits -= m;
-      open = true;
-    }
-    bool done;
-    do {
-      // One group-tested item, branch-free in the common cases: all quantities are derived from a
-      // single 32-bit look at the stream and consumed with ONE skip.
-      const bool active = bits && n < N;
-      const uint32_t g = br.peek32();
-      const bool positive = active && (g & 1u);
-      const uint32_t avail = bits - 1;                       // budget after the test bit
-      const uint32_t room = N - 1 - n;                        // zeros that may precede the one-bit
-      const uint32_t lim = avail < room ? avail : room;
-      const uint32_t gg = g >> 1;
-      const bool found = gg != 0;                             // a one-bit is visible in the window
-      const uint32_t z = found ? (uint32_t)__ffs((int)gg) - 1 : 31u;
-      const bool hit = found && z < lim;                      // an explicit one-bit ends the run
-      if (positive && !hit && lim > 31) {
-        // more than 31 zeros in a row: keep scanning a window at a time (rare)
-        br.skip32(32);
-        bits -= 32;
-        n += 31;
-        uint32_t left = lim - 31;
-        for (;;) {
-          const uint32_t w = br.peek32();
-          const uint32_t step = left < 32 ? left : 32;
-          const uint32_t zz = w ? (uint32_t)__ffs((int)w) - 1 : 32u;
-          if (zz < step) {
-            br.skip32(zz + 1);
-            bits -= zz + 1;
-            n += zz;
-            break;
-          }
-          br.skip32(step);
-          bits -= step;
-          n += step;
-          left -= step;
-          if (!left)
-            break;
-        }
-        x |= 1ull << n;
-        n++;
-        done = !(bits && n < N);  // a following test bit, positive or negative, is the next item
-      }
-      else {
-        const uint32_t c = hit ? z : lim;                     // zeros read (then the one-bit, the last
-                                                              // coefficient or the end of the budget)
-        uint32_t t = positive ? 1 + c + (hit ? 1u : 0u) : (active ? 1u : 0u);
-        const uint32_t n1 = positive ? n + c + 1 : n;
-        x |= positive ? 1ull << ((n + c) & 63) : 0ull;        // deposited even if the scan ran dry
-        const uint32_t bits1 = bits - t;
-        // the plane goes on if coefficients and budget remain; a negative test that is visible in
-        // the same window closes it here, anything else is the next item
-        const bool more = positive && bits1 && n1 < N;
-        const bool closes = more && t < 32 && !((g >> (t & 31)) & 1u);
-        t += closes ? 1u : 0u;
-        br.skip32(t);
-        bits = bits1 - (closes ? 1u : 0u);
-        n = n1;
-        done = !more || closes;
-      }
-    } while (TIGHT && !done);
-    if (done) {
-      sp[(k - kbase) * 32] = (typename PlaneWord<N>::type)x;
-      lowest = k;
-      open = false;
-    }
-  }
-  st.bits = bits;
-  st.n = n;
-  st.x = x;
-  st.open = open;
-  st.k = k;
-  st.lowest = lowest;
-  st.done = finished;
 }
 
 // Plane-lockstep decoder for the column reader, the mirror image of encode_planes_lockstep.  Per
@@ -1257,6 +915,11 @@ __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, 
   bool done = st.done;
   PlaneRec<N> rec = { 0, 0, 0, sp, false };
   while (k > klo && __any_sync(FULL, !done)) {
+    if (br.needs_restage()) {  // variable rate, long blocks: slide the window (positions in rec would go stale)
+      finish_plane<N>(br, rec);
+      rec.store = false;
+      br.restage();
+    }
     decode_plane_lockstep<N>(br, kmin, k - 1, bits, n, lowest, done, sp + (k - 1 - kbase) * 32, rec);
     decode_plane_lockstep<N>(br, kmin, k - 2, bits, n, lowest, done, sp + (k - 2 - kbase) * 32, rec);
     k -= 2;
@@ -1539,30 +1202,6 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     const uint32_t used = bw.tell() - start;
     bits += used < budget ? used : budget;
   }
-  else if constexpr (Writer::kStaged) {
-    // two-phase: the high 32 planes first; the low 32 only if some block of the warp still has
-    // budget when it gets there (all 32 lanes reach the vote: the staged kernel has no early exit)
-    const uint32_t budget = prm.maxbits - bits, start = bw.tell();
-    const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
-    EncodeState st = { 0, 0, P, !coded };
-    if constexpr (P == 64) {
-      to_planes_half<1, UInt, N>(u, sp);
-      if (!st.done)
-        encode_planes_staged<N, REV>(bw, start, budget, kmin, 32, 32, st, sp);
-      if (__any_sync(0xffffffffu, !st.done)) {
-        to_planes_half<0, UInt, N>(u, sp);
-        if (!st.done)
-          encode_planes_staged<N, REV>(bw, start, budget, kmin, 0, 0, st, sp);
-      }
-    }
-    else {
-      to_planes_half<0, UInt, N>(u, sp);
-      if (!st.done)
-        encode_planes_staged<N, REV>(bw, start, budget, kmin, 0, 0, st, sp);
-    }
-    const uint32_t used = bw.tell() - start;
-    bits += used < budget ? used : budget;
-  }
   else if (coded) {
     to_planes<UInt, N>(u, sp);
     bits += encode_planes<N, P>(bw, prm.maxbits - bits, maxprec, sp);
@@ -1633,30 +1272,6 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     }
     else {
       decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);
-      from_planes_half<0, UInt, N>(u, sp, st.lowest);
-    }
-    bits += budget - st.bits;
-  }
-  else if constexpr (Reader::kStaged) {
-    const uint32_t budget = prm.maxbits - bits;
-    const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
-    DecodeState st = { 0, budget, 0, P, P, false, zero };
-#pragma unroll
-    for (int i = 0; i < N; i++)
-      u[i] = 0;
-    if constexpr (P == 64) {
-      if (!st.done)
-        decode_planes_staged<N, REV>(br, kmin, 32, 32, st, sp);
-      from_planes_half<1, UInt, N>(u, sp, st.lowest);
-      if (__any_sync(0xffffffffu, !st.done)) {
-        if (!st.done)
-          decode_planes_staged<N, REV>(br, kmin, 0, 0, st, sp);
-        from_planes_half<0, UInt, N>(u, sp, st.lowest);
-      }
-    }
-    else {
-      if (!st.done)
-        decode_planes_staged<N, REV>(br, kmin, 0, 0, st, sp);
       from_planes_half<0, UInt, N>(u, sp, st.lowest);
     }
     bits += budget - st.bits;

@@ -210,7 +210,7 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 }
 
 // Fixed rate with word-aligned blocks, fast path: bits are staged per lane in shared memory
-// (StageWriter) and leave with 64-bit stores.  Dynamic shared memory per warp:
+// (ColWriter, codec.cuh) and leave with 16-byte stores.  Dynamic shared memory per warp:
 // planes (P*32 plane words) followed by (maxbits/32 + kStageSlack) * 32 staging words.
 #ifndef ZB_MINBLOCKS64
 #define ZB_MINBLOCKS64 5  // launch-bounds hint for the 64-bit staged kernels; 5 measured best of {4,5,6,8} on B200
@@ -266,7 +266,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 
 // Fixed rate, word-aligned blocks, fast path: each lane first copies its block's words to a
 // shared-memory column (all loads in flight at once instead of one dependent global load per
-// word inside the serial decoder), then decodes from there (StageReader).
+// word inside the serial decoder), then decodes from there (ColReader, codec.cuh).
 // decode_staged_kernel: CTA size and CTAs per SM by plane width.  The 64-bit kernels run 6 warps
 // per CTA and rendezvous once after the stream parse: their tail (inverse transposes, lifting, cast)
 // is ~50 KB of straight-line code, far more than the 32 KB instruction cache level, and warps that
@@ -358,7 +358,7 @@ encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g
   typename TR::Scalar v[N];
   gather<DIMS>(v, data, g, pos);
 
-  StageWriter bw;
+  ColWriter bw;
   // lanes past the end write to the last block's slot too; they carry identical bits
   bw.init(stage, slots + (b - block0) * (uint64_t)slot_words32, kVarStageWords);
   const uint32_t bits = encode_block<TYPE, DIMS, REV>(v, prm, bw, sp);
@@ -386,7 +386,7 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
   const uint64_t b = valid ? b_raw : g.nblocks - 1;
   const uint64_t off = offsets[b];
   const uint32_t phase = (uint32_t)(off & 31), len = lengths[b];
-  StageReader br;
+  ColReader br;
   br.init_var(stage, kVarStageWords, in + (off >> 5), (phase + len + 31) >> 5, phase);
   typename TR::Scalar v[N];
   decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
