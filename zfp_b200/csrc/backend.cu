@@ -450,6 +450,126 @@ static zfp_exec_params_cuda* get_cuda_params(const zfp_stream* zfp)
   return p->magic == ZFP_B200_PARAMS_MAGIC ? p : nullptr;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Host-resident field AND host-resident stream at a fixed rate: the transfer is the cost (PCIe),
+// so the array is cut into slabs of whole block layers along its slowest dimension and the slabs
+// are pipelined over a few CUDA streams - H2D of slab i+1, the kernel of slab i and D2H of slab
+// i-1 overlap (both copy engines busy, the kernels hidden).  Fixed-rate slabs sit at deterministic
+// bit offsets; the path is taken when those are word aligned and the field is contiguous.
+// Pinned host buffers give real overlap; pageable ones degrade to the serial order, still correct.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kPipeLanes = 3;
+struct PipeStreams { cudaStream_t s[kPipeLanes] = { nullptr, nullptr, nullptr }; bool ok = false; };
+PipeStreams g_pipe[64];
+
+PipeStreams* pipe_streams()
+{
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_scratch_mutex);
+  PipeStreams& p = g_pipe[dev];
+  if (!p.ok) {
+    for (int i = 0; i < kPipeLanes; i++)
+      if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    p.ok = true;
+  }
+  return &p;
+}
+
+struct SlabPlan {
+  uint32_t slow;            // index of the slowest dimension
+  size_t rows_per_slab;     // extent of a slab along it (multiple of 4)
+  size_t nslabs;
+  size_t elems_per_row;     // values per unit of the slowest dimension
+  uint64_t blocks_per_row4; // blocks per 4 rows
+};
+
+// decide whether (and how) to pipeline; false = use the monolithic path
+bool plan_slabs(const zfp_b200_desc& d, uint64_t start_bit, size_t esize, SlabPlan* plan)
+{
+  if (d.minbits != d.maxbits || d.dims < 2 || (start_bit & 63)) return false;
+  ptrdiff_t expect = 1;
+  for (uint32_t i = 0; i < d.dims; i++) {  // default (contiguous) layout only, implied or spelled out
+    if (d.s[i] != 0 && d.s[i] != expect) return false;
+    expect *= (ptrdiff_t)d.n[i];
+  }
+  const uint32_t slow = d.dims - 1;
+  size_t elems = 1;
+  uint64_t blocks = 1;
+  for (uint32_t i = 0; i < slow; i++) {
+    elems *= d.n[i];
+    blocks *= (d.n[i] + 3) / 4;
+  }
+  const size_t total_bytes = elems * d.n[slow] * esize;
+  if (total_bytes < ((size_t)64 << 20)) return false;  // small arrays: not worth the extra launches
+  // slab size: about 1/16 of the array, at least 16 MiB, whole block layers, word-aligned stream range
+  size_t layers = (d.n[slow] + 3) / 4;
+  size_t per = layers / 16 ? layers / 16 : 1;
+  while (per < layers && per * 4 * elems * esize < ((size_t)16 << 20)) per++;
+  while (per < layers && ((blocks * per * d.maxbits) & 63)) per++;
+  if ((blocks * per * d.maxbits) & 63) return false;
+  plan->slow = slow;
+  plan->rows_per_slab = per * 4;
+  plan->nslabs = (layers + per - 1) / per;
+  plan->elems_per_row = elems;
+  plan->blocks_per_row4 = blocks;
+  return plan->nslabs >= 2;
+}
+
+// returns the number of stream bits produced / consumed, 0 on failure
+uint64_t run_pipelined(const zfp_b200_desc& d, const SlabPlan& plan, size_t esize, char* h_data, uint64_t* h_words, bool encode,
+                       cudaStream_t user)
+{
+  PipeStreams* ps = pipe_streams();
+  if (!ps) return 0;
+  const size_t total_rows = d.n[plan.slow];
+  const size_t field_bytes = plan.elems_per_row * total_rows * esize;
+  const uint64_t total_blocks = plan.blocks_per_row4 * ((total_rows + 3) / 4);
+  const uint64_t total_bits = total_blocks * d.maxbits;
+  const size_t words_bytes = (size_t)((total_bits + 63) >> 6) * 8;
+  char* d_data = static_cast<char*>(scratch(SCR_STAGE_DATA, field_bytes));
+  uint64_t* d_words = static_cast<uint64_t*>(scratch(SCR_STAGE_WORDS, words_bytes + 64));
+  if (!d_data || !d_words) return 0;
+  // everything already enqueued on the caller's stream comes first
+  cudaEvent_t ready;
+  if (!cuda_ok(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming), "event")) return 0;
+  cudaEventRecord(ready, user);
+  for (int i = 0; i < kPipeLanes; i++)
+    cudaStreamWaitEvent(ps->s[i], ready, 0);
+  bool ok = true;
+  for (size_t i = 0; i < plan.nslabs && ok; i++) {
+    cudaStream_t st = ps->s[i % kPipeLanes];
+    const size_t row0 = i * plan.rows_per_slab;
+    const size_t rows = row0 + plan.rows_per_slab <= total_rows ? plan.rows_per_slab : total_rows - row0;
+    const size_t off = row0 * plan.elems_per_row * esize, bytes = rows * plan.elems_per_row * esize;
+    const uint64_t bit0 = (uint64_t)(row0 / 4) * plan.blocks_per_row4 * d.maxbits;
+    const uint64_t nbits = (uint64_t)((rows + 3) / 4) * plan.blocks_per_row4 * d.maxbits;
+    const size_t w0 = (size_t)(bit0 >> 6), nw = (size_t)((nbits + 63) >> 6);
+    zfp_b200_desc slab = d;
+    slab.n[plan.slow] = rows;
+    slab.s[0] = slab.s[1] = slab.s[2] = slab.s[3] = 0;
+    uint64_t end = 0;
+    if (encode) {
+      ok = cuda_ok(cudaMemcpyAsync(d_data + off, h_data + off, bytes, cudaMemcpyHostToDevice, st), "H2D slab") &&
+           zfp_b200_encode(&slab, d_data + off, d_words + w0, 0, &end, nullptr, st) == ZFP_B200_OK &&
+           cuda_ok(cudaMemcpyAsync(h_words + w0, d_words + w0, nw * 8, cudaMemcpyDeviceToHost, st), "D2H slab stream");
+    }
+    else {
+      ok = cuda_ok(cudaMemcpyAsync(d_words + w0, h_words + w0, nw * 8, cudaMemcpyHostToDevice, st), "H2D slab stream") &&
+           zfp_b200_decode(&slab, d_data + off, d_words + w0, 0, &end, nullptr, st) == ZFP_B200_OK &&
+           cuda_ok(cudaMemcpyAsync(h_data + off, d_data + off, bytes, cudaMemcpyDeviceToHost, st), "D2H slab");
+    }
+  }
+  for (int i = 0; i < kPipeLanes; i++)
+    ok = cuda_ok(cudaStreamSynchronize(ps->s[i]), "sync") && ok;
+  cudaEventDestroy(ready);
+  return ok ? total_bits : 0;
+}
+
+}  // namespace
+
 static size_t compress_impl(zfp_stream* zfp, const zfp_field* field)
 {
   zfp_b200_desc d;
@@ -460,6 +580,19 @@ static size_t compress_impl(zfp_stream* zfp, const zfp_field* field)
   const size_t esize = scalar_bytes(d.type);
   const uint64_t start_bit = (uint64_t)(s->ptr - s->begin) * 64 + s->bits;
   const uint64_t first_word = start_bit >> 6;
+
+  // host field, host stream, fixed rate: slab pipeline over the copy engines
+  SlabPlan plan;
+  if (!on_device(field->data) && !on_device(s->begin) && !s->bits && !getenv("ZFP_B200_NO_PIPELINE") &&
+      plan_slabs(d, start_bit, esize, &plan)) {
+    const uint64_t bits = run_pipelined(d, plan, esize, static_cast<char*>(const_cast<void*>(field->data)), s->begin + first_word,
+                                        true, st);
+    if (!bits) return 0;
+    s->ptr = s->begin + first_word + ((bits + 63) >> 6);
+    s->bits = 0;
+    s->buffer = 0;
+    return (size_t)(s->ptr - s->begin) * 8;
+  }
 
   // field data: use in place when device resident, else stage the touched span
   int64_t lo, hi;
@@ -524,6 +657,16 @@ static size_t decompress_impl(zfp_stream* zfp, zfp_field* field)
   const size_t esize = scalar_bytes(d.type);
   const uint64_t start_bit = (uint64_t)(s->ptr - s->begin) * 64 - s->bits;
   const uint64_t first_word = start_bit >> 6;
+
+  SlabPlan plan;
+  if (!on_device(field->data) && !on_device(s->begin) && !getenv("ZFP_B200_NO_PIPELINE") && plan_slabs(d, start_bit, esize, &plan)) {
+    const uint64_t bits = run_pipelined(d, plan, esize, static_cast<char*>(field->data), s->begin + first_word, false, st);
+    if (!bits) return 0;
+    s->ptr = s->begin + first_word + ((bits + 63) >> 6);
+    s->bits = 0;
+    s->buffer = 0;
+    return (size_t)(s->ptr - s->begin) * 8;
+  }
 
   int64_t lo, hi;
   index_span(&d, &lo, &hi);
