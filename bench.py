@@ -58,20 +58,57 @@ def field_slab(torch, rank, nz, ny, nx, device):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML
+    polled every ~5 ms in a thread (nvidia-smi -lms as the fallback); only samples taken between
+    mark_begin() and mark_end() count."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.t0 = self.t1 = None
+        self.max_mhz = None
+        self.how = None
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.how = "nvml"
+            while not self.stop_flag:
+                t = time.perf_counter()
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((t, mhz, mask))
+                time.sleep(0.005)
+            return
+        except Exception:
+            pass
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
+        try:
+            self.how = "nvidia-smi"
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([v.strip() for v in line.split(",")])
+                r = [v.strip() for v in line.split(",")]
+                if len(r) >= 6 and r[0].replace(".", "").isdigit():
+                    self.max_mhz = float(r[1])
+                    mask = sum(b for b, v in zip(bits, r[2:6]) if v.lower().startswith("active"))
+                    self.rows.append((time.perf_counter(), float(r[0]), mask))
                 if self.stop_flag:
                     break
         except Exception:
@@ -81,12 +118,14 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self.join(timeout=2)
+        inside = [r for r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        use = inside if inside else self.rows[-3:]
+        mask = 0
+        for r in use:
+            mask |= r[2]
+        return {"sm_mhz": float(np.median([r[1] for r in use])) if use else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b), "samples": len(inside), "source": self.how}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -197,11 +236,13 @@ def run_ours(args):
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     t_begin.record()
     for i in range(args.steps):
         c = step(evs[i])
     t_end.record()
     barrier()
+    sampler.mark_end()
     launches = zb.launch_count() - launches0
     clocks = sampler.finish()
     total_ms = t_begin.elapsed_time(t_end)

@@ -733,12 +733,14 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
     bw.append32((uint32_t)verb, n);
   // every one-bit moved up by its rank: b0 + 2 b1 + 4 b2 + 8 b3 + ... = y + r1 + 2 r2 + 4 r3 + ...
   uint32_t yp = y32 + r1 + 2 * r2 + 4 * r3;
-  if (__any_sync(FULL, r4 != 0)) {
+  // one vote on the common path: more than four new coefficients, or a T that does not fit 32 bits
+  bool fast = true;
+  if (__any_sync(FULL, slow || r4 != 0)) {
     const uint32_t r5 = r4 & (r4 - 1), r6 = r5 & (r5 - 1), r7 = r6 & (r6 - 1), r8 = r7 & (r7 - 1);
     yp += 8 * r4 + 16 * r5 + 32 * r6 + 64 * r7;
-    slow = slow || r8 != 0;
+    fast = !__any_sync(FULL, slow || r8 != 0);
   }
-  if (!__any_sync(FULL, slow)) {
+  if (fast) {
     const bool has = y32 != 0;
     const uint32_t top = n + (uint32_t)(msb + 1);    // coefficients settled after this plane
     const uint32_t last = (has && top == N) ? 1u : 0u;
@@ -893,9 +895,10 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   const uint32_t s = wv & ~(wv << 1);                    // run starts
   const uint32_t ae = wv + (s & 0x55555555u), ao = wv + (s & 0xaaaaaaaau);
   const uint32_t term = (ae & ~wv & 0xaaaaaaaau) | (ao & ~wv & 0x55555555u);  // just past each odd-length run
-  const uint32_t tpos = (uint32_t)__ffs((int)term) - 1;  // bits of T (0xffffffff when no end in the window)
-  uint32_t d = ((wv & ~ae & 0x55555554u) | (wv & ~ao & 0xaaaaaaaau)) & mask32(tpos);  // data bits of T, virtual one dropped
-  d = test ? d : 0u;
+  const uint32_t tl = term & (0u - term);                // lowest end mark; tl - 1 masks the bits of T
+  const uint32_t tpos = 31u - (uint32_t)__clz((int)tl);  // bits of T (0xffffffff when no end in the window)
+  // data bits of T (virtual one dropped); nothing when there is no group test
+  const uint32_t d = ((wv & ~ae & 0x55555554u) | (wv & ~ao & 0xaaaaaaaau)) & (tl - 1) & (test ? ~0u : 0u);
   const uint32_t c = (uint32_t)__popc(d);
   const uint32_t ntop = n + (uint32_t)(31 - __clz((int)d)) - c;  // n + (msb(d) - 2 - (c-1)) + 1: coefficients settled if c > 0
   // data bits two places down (the virtual bit and the first test), then each moved down by its rank:
@@ -904,12 +907,14 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   bool slow = test && (term == 0 || tpos > left || (c != 0 && ntop > N - 1));
   uint32_t y = d0 - (d1 >> 1) - (d2 >> 2) - (d3 >> 3);
   finish_plane<N>(br, prev);  // the previous plane's leftover work: independent of everything above
-  if (__any_sync(FULL, d4 != 0)) {
+  // one vote on the common path: more than four new coefficients, or something the shortcut cannot prove
+  bool fast = true;
+  if (__any_sync(FULL, slow || d4 != 0)) {
     const uint32_t d5 = d4 & (d4 - 1), d6 = d5 & (d5 - 1), d7 = d6 & (d6 - 1), d8 = d7 & (d7 - 1);
     y -= (d4 >> 4) + (d5 >> 5) + (d6 >> 6) + (d7 >> 7);
-    slow = slow || d8 != 0;
+    fast = !__any_sync(FULL, slow || d8 != 0);
   }
-  if (!__any_sync(FULL, slow)) {
+  if (fast) {
     if constexpr (N > 32)
       rec.ybits = shl64c((uint64_t)y, n);
     else
