@@ -42,6 +42,22 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(md_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this exact workload, from
+    the `ncu --set full` capture summarised under profiles/ (a profiler run, not this run); None if absent."""
+    path = os.path.join(ROOT, "profiles", md_name)
+    try:
+        with open(path) as f:
+            for line in f:
+                if line.startswith("| traffic (dram read+write)"):
+                    cells = [c.strip() for c in line.strip().strip("|").split("|")]
+                    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(cells[2], None)
+                    return float(cells[1]) * scale if scale else None
+    except OSError:
+        pass
+    return None
+
+
 def field_slab(torch, rank, nz, ny, nx, device):
     """SURVEY 8(d) S1 analytic smooth field, slab `rank` of the global array, generated on device."""
     gz = torch.arange(rank * nz, (rank + 1) * nz, device=device, dtype=torch.float64) / (nz * max(1, int(os.environ.get("WORLD_SIZE", "1"))) - 1)
@@ -310,11 +326,13 @@ def run_ours(args):
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch on this exact workload, from the ncu
     # --set full captures summarised in profiles/ (a profiler run, not this run)
     roof_enc = {"kernel": "encode_staged_kernel<double,3>", "bound": "hbm", "achieved": enc_alg / (enc_ms * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "traffic": 9.6633e9, "traffic_source": "profiles/r1_encode_staged_fp64_r8_1024cubed.md",
+                "peak": peak, "unit": "GB/s", "traffic": profiled_traffic("r1_encode_staged_fp64_r8_1024cubed.md"),
+                "traffic_source": "profiles/r1_encode_staged_fp64_r8_1024cubed.md",
                 "algorithmic_bytes": enc_alg, "peak_source": peak_src, "ms": enc_ms}
     roof_enc["frac"] = roof_enc["achieved"] / peak
     roof_dec = {"kernel": "decode_staged_kernel<double,3>", "bound": "hbm", "achieved": dec_alg / (dec_ms * 1e-3) / 1e9,
-                "peak": peak, "unit": "GB/s", "traffic": 10.4102e9, "traffic_source": "profiles/r1_decode_staged_fp64_r8_1024cubed.md",
+                "peak": peak, "unit": "GB/s", "traffic": profiled_traffic("r1_decode_staged_fp64_r8_1024cubed.md"),
+                "traffic_source": "profiles/r1_decode_staged_fp64_r8_1024cubed.md",
                 "algorithmic_bytes": dec_alg, "peak_source": peak_src, "ms": dec_ms}
     roof_dec["frac"] = roof_dec["achieved"] / peak
     dominant = roof_dec if dec_ms >= enc_ms else roof_enc
