@@ -36,7 +36,7 @@ def build(ref=True):
     have_ref = ref and os.path.isdir(os.environ.get("ZFP_REFERENCE", "/root/reference"))
     targets = ["port"] + (["ref"] if have_ref else [])
     if have_ref and os.path.exists(os.path.join(HERE, "..", "zfp_b200", "lib", "libzfp_b200.so")):
-        targets.append("ref_cuda")
+        targets += ["ref_cuda", "ref_cli"]
     subprocess.check_call(["make", "-s", "-C", HERE] + targets)
 
 

@@ -279,6 +279,37 @@ def test_reference_library_with_our_backend_as_its_cuda_policy(port):
             assert out.tobytes() == R.decompress(serial, a.shape, a.dtype, **mode).tobytes()
 
 
+def test_reference_cli_on_our_backend_c1(tmp_path):
+    """BASELINE.json configs[0]: 3-D double 256^3, fixed rate 8, through the reference's own `zfp`
+    command-line tool (utils/zfp.c, unmodified).  The tool linked against the drop-in library and run
+    with `-x cuda -h` must write the same file, header included, as the stock CPU tool with
+    `-x serial` (the reference's CUDA backend overwrites headers, docs/source/execution.rst:203-204;
+    ours honours the stream offset), and decompress it to the same bytes."""
+    import subprocess
+    from oracle.oracle import HERE as ORACLE_DIR
+    cpu, gpu = os.path.join(ORACLE_DIR, "_ref", "zfp_ref"), os.path.join(ORACLE_DIR, "_ref", "zfp_ref_cuda")
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref/zfp_ref[_cuda] not built")
+    a = analytic_field((256, 256, 256), np.float64)
+    raw = tmp_path / "field.raw"
+    a.tofile(raw)
+    outs = {}
+    for name, exe, policy in (("cpu", cpu, "serial"), ("gpu", gpu, "cuda")):
+        z, o = tmp_path / (name + ".zfp"), tmp_path / (name + ".out")
+        r = subprocess.run([exe, "-d", "-3", "256", "256", "256", "-r", "8", "-h", "-x", policy, "-i", str(raw), "-z", str(z), "-o", str(o)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        outs[name] = (z.read_bytes(), o.read_bytes())
+    assert len(outs["gpu"][0]) == 16 + 256 ** 3  # 96-bit header rounded up to words + 8 bits/value
+    assert outs["gpu"][0] == outs["cpu"][0], "compressed files differ"
+    assert outs["gpu"][1] == outs["cpu"][1], "decompressed files differ"
+    # and the GPU tool decompresses the CPU tool's file (header parsed, payload mid-word)
+    o2 = tmp_path / "cross.out"
+    r = subprocess.run([gpu, "-h", "-x", "cuda", "-z", str(tmp_path / "cpu.zfp"), "-o", str(o2)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert o2.read_bytes() == outs["cpu"][1]
+
+
 def test_zfpy_compatible_module_interoperates_with_reference(zb, ref):
     """zfp_b200.zfpy: same signatures and byte format as the reference's zfpy (python/zfpy.pyx);
     streams with full headers travel both ways, with and without our index trailer."""
