@@ -84,6 +84,15 @@ int zfp_b200_encode(const zfp_b200_desc* desc, const void* d_data, void* d_words
 int zfp_b200_decode(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
                     uint64* end_bit, const zfp_b200_index* index, void* cuda_stream);
 
+/* Random access: decode only blocks [block0, block1) of the stream (stream order, x fastest:
+ * b = bx + BX*(by + BY*(bz + BZ*bw)), src/template/ompcompress.c:168-198) into their places in the
+ * field at d_data; values of other blocks are left untouched.  Fixed rate needs no index (block b
+ * starts at start_bit + b*maxbits); variable rate uses the block-offset index (NULL = rebuild it by
+ * scanning the stream).  This is the parallel form of what the reference offers only through its
+ * C++ compressed-array classes (include/zfp/index.hpp:160-530). */
+int zfp_b200_decode_blocks(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
+                           uint64 block0, uint64 block1, const zfp_b200_index* index, void* cuda_stream);
+
 /* Bit-granular device copy dst[dst_bit, dst_bit+nbits) = src[src_bit, ...): places a slab stream
  * produced at another bit phase / on another GPU into a global stream.  Destination words fully
  * inside the range are overwritten, partially covered ones OR-merged (their target bits must be 0). */

@@ -279,6 +279,42 @@ def test_reference_library_with_our_backend_as_its_cuda_policy(port):
             assert out.tobytes() == R.decompress(serial, a.shape, a.dtype, **mode).tobytes()
 
 
+@pytest.mark.parametrize("dtype,shape", [(np.float64, (40, 44, 52)), (np.float32, (70, 90)), (np.int32, (300,)),
+                                         (np.float64, (8, 12, 8, 9))])
+def test_random_access_block_range_decode(zb, dtype, shape):
+    """zfp_b200_decode_blocks: any range of blocks decodes in parallel into its place and leaves the
+    rest of the array untouched - fixed rate straight from the block number, variable rate through
+    the block-offset index."""
+    import torch
+    a = analytic_field(shape, dtype)
+    x = torch.from_numpy(a).cuda()
+    nblocks = int(np.prod([(n + 3) // 4 for n in shape]))
+    sentinel = 77
+    modes = [{"rate": 8}, {"rate": 5.3}, {"precision": 20}, {"reversible": True}]
+    if np.dtype(dtype).kind == "f":
+        modes.append({"accuracy": 1e-4})
+    for mode in modes:
+        c = zb.compress(x, **mode)
+        full = zb.decompress(c)
+        # which block every element belongs to (stream order: x fastest)
+        idx = np.zeros(shape, dtype=np.int64)
+        mul = 1
+        for ax in range(len(shape) - 1, -1, -1):
+            coord = np.arange(shape[ax]) // 4
+            view = [1] * len(shape)
+            view[ax] = shape[ax]
+            idx += coord.reshape(view) * mul
+            mul *= (shape[ax] + 3) // 4
+        owner = torch.from_numpy(idx).cuda()
+        for b0, b1 in ((0, 1), (nblocks // 3, nblocks // 3 + 37 if nblocks > 80 else nblocks // 2 + 1), (nblocks - 1, nblocks),
+                       (5, 5), (0, nblocks)):
+            out = torch.full_like(full, sentinel)
+            zb.decompress_blocks(c, b0, b1, out)
+            inside = (owner >= b0) & (owner < b1)
+            assert torch.equal(out[inside], full[inside]), (mode, b0, b1)
+            assert bool((out[~inside] == sentinel).all()), (mode, b0, b1)
+
+
 def test_reference_cli_on_our_backend_c1(tmp_path):
     """BASELINE.json configs[0]: 3-D double 256^3, fixed rate 8, through the reference's own `zfp`
     command-line tool (utils/zfp.c, unmodified).  The tool linked against the drop-in library and run

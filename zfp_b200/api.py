@@ -85,6 +85,7 @@ _PROTOTYPES = {
     "zfp_stream_cuda_params": (C.POINTER(CudaParams), [_vp]),
     "zfp_b200_encode": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp]),
     "zfp_b200_decode": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp]),
+    "zfp_b200_decode_blocks": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "zfp_b200_bitcopy": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]),
     "zfp_b200_is_fixed_rate": (C.c_int, [C.POINTER(Desc)]), "zfp_b200_blocks": (_sz, [C.POINTER(Desc)]),
     "zfp_b200_capacity": (_sz, [C.POINTER(Desc), C.c_uint64]),
@@ -316,6 +317,28 @@ def decompress(c, out=None, header=False):
         raise RuntimeError("zfp_decompress failed: %s" % last_error())
     if nbytes != c.nbytes:
         raise RuntimeError("zfp_decompress consumed %d bytes, compress produced %d" % (nbytes, c.nbytes))
+    return out
+
+
+def decompress_blocks(c, block0, block1, out):
+    """Random access: decode blocks [block0, block1) (stream order, x fastest) of a `Compressed` into
+    their places in the CUDA tensor `out` (same shape / dtype as the compressed array); everything
+    else in `out` is left as it is.  Variable-rate streams use the block index kept with `c`."""
+    L = load_library()
+    zt = _tensor_type(out)
+    minbits, maxbits, maxprec, minexp = mode_params(c.mode, str(out.dtype).split(".")[-1], out.dim())
+    d = Desc()
+    d.type, d.dims = zt, out.dim()
+    for i, (n, st) in enumerate(zip(reversed(out.shape), reversed(out.stride()))):
+        d.n[i], d.s[i] = n, st
+    d.minbits, d.maxbits, d.maxprec, d.minexp = minbits, maxbits, maxprec, minexp
+    index = None
+    if minbits != maxbits:
+        p = L.zfp_stream_cuda_params(c.stream.z)
+        index = p.contents.index if p else None
+    rc = L.zfp_b200_decode_blocks(C.byref(d), out.data_ptr(), c.words.data_ptr(), c.start_bit, block0, block1, index, None)
+    if rc:
+        raise RuntimeError("zfp_b200_decode_blocks failed (%d): %s" % (rc, last_error()))
     return out
 
 

@@ -223,10 +223,11 @@ static int encode_any(int out_mode, int type, uint32_t dims, const void* data, c
 }
 
 static int decode_any(int offs_mode, int type, uint32_t dims, void* data, const Geom& g, const Params& prm, const void* in,
-                      uint64_t start_bit, const uint64_t* offsets, const uint16_t* lengths, cudaStream_t st)
+                      uint64_t start_bit, const uint64_t* offsets, const uint16_t* lengths, cudaStream_t st, uint64_t b0, uint64_t b1)
 {
   static const int staged = getenv("ZFP_B200_NO_STAGED") ? 0 : 1;
-  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, lengths, st, staged };
+  if (b0 >= b1) return ZFP_B200_OK;
+  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, lengths, st, staged, b0, b1 };
   cudaError_t e;
   switch (type) {
     case T_INT32: e = launch_decode_t<T_INT32>((int)dims, offs_mode, a); break;
@@ -333,8 +334,23 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
   return ZFP_B200_OK;
 }
 
+static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit, uint64* end_bit,
+                        const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole);
+
 extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
                                uint64* end_bit, const zfp_b200_index* index, void* cuda_stream)
+{
+  return decode_range(d, d_data, d_words, start_bit, end_bit, index, cuda_stream, 0, 0, true);
+}
+
+extern "C" int zfp_b200_decode_blocks(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
+                                      uint64 block0, uint64 block1, const zfp_b200_index* index, void* cuda_stream)
+{
+  return decode_range(d, d_data, d_words, start_bit, nullptr, index, cuda_stream, block0, block1, false);
+}
+
+static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit, uint64* end_bit,
+                        const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole)
 {
   Geom g;
   if (!make_geom(d, d_data, &g) || !check_params(d) || !d_data || !d_words) {
@@ -344,9 +360,17 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
   int rc;
+  if (whole) {
+    block0 = 0;
+    block1 = g.nblocks;
+  }
+  else if (block0 > block1 || block1 > g.nblocks) {
+    g_error = "zfp_b200_decode_blocks: block range outside the field";
+    return ZFP_B200_EINVAL;
+  }
 
   if (d->minbits == d->maxbits) {
-    rc = decode_any(0, d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, nullptr, st);
+    rc = decode_any(0, d->type, d->dims, d_data, g, prm, d_words, start_bit, nullptr, nullptr, st, block0, block1);
     if (rc) return rc;
     if (end_bit) *end_bit = start_bit + g.nblocks * (uint64_t)d->maxbits;
     return ZFP_B200_OK;
@@ -363,7 +387,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
     // foreign stream: rebuild the index by parsing the stream sequentially on the device
     uint16_t* rebuilt = static_cast<uint16_t*>(scratch(SCR_LENGTHS, g.nblocks * sizeof(uint16_t)));
     if (!rebuilt) return ZFP_B200_ECUDA;
-    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, nullptr, st, 0 };
+    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, nullptr, st, 0, 0, g.nblocks };
     cudaError_t e;
     switch (d->type) {
       case T_INT32: e = launch_index_t<T_INT32>((int)d->dims, a, rebuilt); break;
@@ -383,7 +407,7 @@ extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void*
   LAUNCHED();
   rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st);
   if (rc) return rc;
-  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st);
+  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st, block0, block1);
   if (rc) return rc;
   uint64_t h_cursor[2];
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));

@@ -71,9 +71,9 @@ cudaError_t run_decode_var(const DecodeArgs& a)
   constexpr size_t smem = var_smem_bytes<TYPE, DIMS>();
   cudaError_t e = allow_smem(kernel, smem);
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
+  const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;
   kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
-                                                    static_cast<const uint32_t*>(a.in), a.offsets, a.lengths);
+                                                    static_cast<const uint32_t*>(a.in), a.offsets, a.lengths, a.b0, a.b1);
   return cudaGetLastError();
 }
 
@@ -111,9 +111,9 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
     if (e != cudaSuccess) return e;
     allowed = smem;
   }
-  const uint64_t ctas = (a.g.nblocks + DecCfg<TYPE>::threads - 1) / DecCfg<TYPE>::threads;
+  const uint64_t ctas = (a.b1 - a.b0 + DecCfg<TYPE>::threads - 1) / DecCfg<TYPE>::threads;
   kernel<<<(unsigned)ctas, DecCfg<TYPE>::threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
-                                                    static_cast<const uint64_t*>(a.in), a.start_bit);
+                                                    static_cast<const uint64_t*>(a.in), a.start_bit, a.b0, a.b1);
   return cudaGetLastError();
 }
 
@@ -132,9 +132,9 @@ cudaError_t run_decode(const DecodeArgs& a)
   constexpr size_t smem = plane_smem_bytes<TYPE, DIMS>();
   cudaError_t e = allow_smem(kernel, smem);
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
+  const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;
   kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
-                                                    a.start_bit, a.offsets);
+                                                    a.start_bit, a.offsets, a.b0, a.b1);
   return cudaGetLastError();
 }
 
@@ -150,9 +150,9 @@ cudaError_t run_encode4(const EncodeArgs& a)
 template <int TYPE, int OFFS>
 cudaError_t run_decode4(const DecodeArgs& a)
 {
-  const unsigned ctas = (unsigned)((a.g.nblocks + kThreads4 - 1) / kThreads4);
+  const unsigned ctas = (unsigned)((a.b1 - a.b0 + kThreads4 - 1) / kThreads4);
   decode4_kernel<TYPE, OFFS><<<ctas, kThreads4, 0, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
-                                                            a.start_bit, a.offsets);
+                                                            a.start_bit, a.offsets, a.b0, a.b1);
   return cudaGetLastError();
 }
 

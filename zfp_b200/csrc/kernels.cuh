@@ -280,7 +280,7 @@ constexpr int kReadSlack = 5;  // zero words after the block: a plane's reads re
 template <int TYPE, int DIMS, bool REV>
 __global__ void __launch_bounds__(DecCfg<TYPE>::threads, DecCfg<TYPE>::min_ctas(REV))
 decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
-                     const uint64_t* __restrict__ in, uint64_t start_bit)
+                     const uint64_t* __restrict__ in, uint64_t start_bit, uint64_t block0, uint64_t block1)
 {
   using TR = Traits<TYPE>;
   constexpr int N = 1 << (2 * DIMS);
@@ -292,9 +292,9 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
   uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
 
-  const uint64_t b_raw = (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
-  const bool valid = b_raw < g.nblocks;  // no early exit (warp-wide votes in decode_block)
-  const uint64_t b = valid ? b_raw : g.nblocks - 1;
+  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
+  const bool valid = b_raw < block1;  // no early exit (warp-wide votes in decode_block)
+  const uint64_t b = valid ? b_raw : block1 - 1;
   const uint64_t* src = in + (start_bit >> 6) + b * (uint64_t)(words >> 1);
   if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const uint4* src4 = reinterpret_cast<const uint4*>(src);
@@ -370,7 +370,7 @@ encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g
 template <int TYPE, int DIMS, bool REV>
 __global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
 decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm, const uint32_t* __restrict__ in,
-                  const uint64_t* __restrict__ offsets, const uint16_t* __restrict__ lengths)
+                  const uint64_t* __restrict__ offsets, const uint16_t* __restrict__ lengths, uint64_t block0, uint64_t block1)
 {
   using TR = Traits<TYPE>;
   constexpr int N = 1 << (2 * DIMS);
@@ -381,9 +381,9 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
   uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
 
-  const uint64_t b_raw = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = b_raw < g.nblocks;
-  const uint64_t b = valid ? b_raw : g.nblocks - 1;
+  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool valid = b_raw < block1;
+  const uint64_t b = valid ? b_raw : block1 - 1;
   const uint64_t off = offsets[b];
   const uint32_t phase = (uint32_t)(off & 31), len = lengths[b];
   ColReader br;
@@ -400,7 +400,8 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
 template <int TYPE, int DIMS, int OFFS, bool REV>
 __global__ void __launch_bounds__(kThreads)
 decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
-              const void* __restrict__ in, uint64_t start_bit, const uint64_t* __restrict__ offsets)
+              const void* __restrict__ in, uint64_t start_bit, const uint64_t* __restrict__ offsets, uint64_t block0,
+              uint64_t block1)
 {
   using TR = Traits<TYPE>;
   constexpr int N = 1 << (2 * DIMS);
@@ -408,8 +409,8 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   extern __shared__ uint64_t smem_raw[];
   PW* sp = reinterpret_cast<PW*>(smem_raw) + (threadIdx.x >> 5) * (TR::P * 32) + (threadIdx.x & 31);
 
-  const uint64_t b = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (b >= g.nblocks)
+  const uint64_t b = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (b >= block1)
     return;
   BitReader br;
   br.init(in, OFFS ? offsets[b] : start_bit + b * (uint64_t)prm.maxbits);

@@ -335,15 +335,15 @@ encode4_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
 template <int TYPE, int OFFS>
 __global__ void __launch_bounds__(kThreads4)
 decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm, const void* __restrict__ in,
-               uint64_t start_bit, const uint64_t* __restrict__ offsets)
+               uint64_t start_bit, const uint64_t* __restrict__ offsets, uint64_t block0, uint64_t block1)
 {
   using TR = Traits<TYPE>;
   using Scalar = typename TR::Scalar;
   using Int = typename TR::Int;
   using UInt = typename TR::UInt;
   constexpr int P = TR::P;
-  const uint64_t b = (uint64_t)blockIdx.x * kThreads4 + threadIdx.x;
-  if (b >= g.nblocks) return;
+  const uint64_t b = block0 + (uint64_t)blockIdx.x * kThreads4 + threadIdx.x;
+  if (b >= block1) return;
 
   Scalar v[256];
   Int q[256];

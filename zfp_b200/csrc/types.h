@@ -49,6 +49,7 @@ struct DecodeArgs {
   const uint16_t* lengths;  // OFFS 1: coded length of every block (bounds the staged reads)
   cudaStream_t st;
   int staged;       // OFFS 0 only: use the shared-memory staged fast path when the stream is word aligned
+  uint64_t b0, b1;  // block range [b0, b1) to decode (random access); the whole field is [0, nblocks)
 };
 
 // one translation unit per scalar type and direction (inst_*.cu) defines these
