@@ -3,6 +3,8 @@
 // 100+ kernel instances compile in parallel.
 #pragma once
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "kernels4d.cuh"
 
@@ -83,9 +85,10 @@ cudaError_t run_encode(const EncodeArgs& a)
   if constexpr (OUT == 0)
     if (a.staged && a.prm.maxbits <= kStagedMaxBits && a.b0 == 0 && a.b1 == a.g.nblocks)
       return run_encode_staged<TYPE, DIMS, REV>(a);
-  // reversible mode keeps the general kernels: its residual planes are noisy (many runs per plane),
-  // where the flattened staged loop measured slower (int32 3-D 1024^3: 6.3 ms vs 4.9 ms)
-  if constexpr (OUT == 2 && !REV)
+  // (measured at 1024^3 / 512^3: reversible int32, whose planes below the common precision are dense
+  // noise from the first coded plane on, is the one case where the general kernel's per-plane run
+  // loop beats the lockstep coder's per-item fallback; float, double and int64 are faster here)
+  if constexpr (OUT == 2 && (!REV || TYPE != T_INT32))
     if (a.staged)
       return run_encode_var<TYPE, DIMS, REV>(a);
   auto kernel = encode_kernel<TYPE, DIMS, OUT, REV>;
@@ -123,9 +126,7 @@ cudaError_t run_decode(const DecodeArgs& a)
   if constexpr (OFFS == 0)
     if (a.staged && a.prm.maxbits <= kStagedMaxBits && (a.prm.maxbits & 63) == 0 && (a.start_bit & 63) == 0)
       return run_decode_staged<TYPE, DIMS, REV>(a);
-  // (measured on 1024^3: reversible int32 decodes faster with the general kernel, reversible
-  // fp64 / int64 with the staged one)
-  if constexpr (OFFS == 1 && (!REV || Traits<TYPE>::P == 64))
+  if constexpr (OFFS == 1 && (!REV || TYPE != T_INT32))
     if (a.staged && a.lengths)
       return run_decode_var<TYPE, DIMS, REV>(a);
   auto kernel = decode_kernel<TYPE, DIMS, OFFS, REV>;
