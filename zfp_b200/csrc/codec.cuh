@@ -1217,6 +1217,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   }
 
   UInt u[N];
+  UInt any = 0;  // reversible mode: OR of all coefficients
   if (!reversible) {
     xform_fwd<0, DIMS>(q);
 #pragma unroll
@@ -1225,7 +1226,6 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   }
   else {
     xform_fwd<2, DIMS>(q);
-    UInt any = 0;
 #pragma unroll
     for (int i = 0; i < N; i++) {
       u[i] = int2uint(q[perm_at<DIMS>(i)]);
@@ -1246,25 +1246,46 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     const uint32_t budget = prm.maxbits - bits, start = bw.tell();
     const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
     LockState st = { 0, P, !coded };
+    if constexpr (REV) {
+      // Reversible residuals leave many high planes empty.  With no coefficient significant yet an
+      // empty plane codes as a lone '0' test, so the planes above the warp's highest occupied plane
+      // go out in one append and the lockstep walk starts below them (two planes per step: even k).
+      const int top = any ? (P == 64 ? 63 - __clzll((long long)any) : 31 - __clz((int)any)) : -1;
+      int first = coded ? top + 1 : 0;                 // planes >= first are empty in this block
+      if (coded && budget < (uint32_t)P) first = P;    // the budget could bind: no shortcut
+      int kstart = (int)__reduce_max_sync(0xffffffffu, (unsigned)first);
+      kstart = (kstart + 1) & ~1;
+      if (kstart < P) {
+        const int lo = kstart > kmin ? kstart : kmin;  // this block codes planes P-1 .. lo as '0'
+        bw.append64(0, 0, (coded && lo < P) ? (uint32_t)(P - lo) : 0u);
+        st.k = kstart;
+      }
+    }
     if constexpr (P == 64 && N == 64) {
       // the high 32 planes as one half, then the low half as two windows of 16 planes, each only if
       // some block of the warp still has planes and budget left when it gets there (all 32 lanes
       // reach the votes: the lockstep kernels have no early exit).  Measured on 1024^3 fp64:
       // blocks that stop within the high half (accuracy 1e-6, precision 32) are fastest with an
       // undivided half, blocks that go a few planes further (rate 8) with a 16-plane window.
-      to_planes_half<1, UInt, N>(u, sp);
-      encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+      if (st.k > 32) {
+        to_planes_half<1, UInt, N>(u, sp);
+        encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+      }
 #pragma unroll 1
       for (int w = 1; w >= 0; w--) {
         if (!__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < start + budget))
           break;
+        if (st.k <= 16 * w)
+          continue;
         to_planes_window<0>(u, sp, (uint32_t)w);
         encode_planes_lockstep<N>(bw, start + budget, kmin, 16 * w, 16 * w, st, sp);
       }
     }
     else if constexpr (P == 64) {
-      to_planes_half<1, UInt, N>(u, sp);
-      encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+      if (st.k > 32) {
+        to_planes_half<1, UInt, N>(u, sp);
+        encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+      }
       if (__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < start + budget)) {
         to_planes_half<0, UInt, N>(u, sp);
         encode_planes_lockstep<N>(bw, start + budget, kmin, 0, 0, st, sp);
@@ -1336,6 +1357,23 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
 #pragma unroll
     for (int i = 0; i < N; i++)
       u[i] = 0;
+    if constexpr (REV) {
+      // mirror of the encoder's shortcut: leading '0' tests while no coefficient is significant are
+      // empty planes; the warp skips the ones all its blocks have in common (even count, at most the
+      // 32 planes of the first window, stored as zeros)
+      const uint32_t w0 = br.peek32(br.bp);
+      const uint32_t lim = st.bits < (uint32_t)(P - kmin) ? st.bits : (uint32_t)(P - kmin);
+      uint32_t z = w0 ? (uint32_t)__ffs((int)w0) - 1 : 32u;
+      z = zero ? 32u : (z < lim ? z : lim);
+      const uint32_t skip = __reduce_min_sync(0xffffffffu, z) & ~1u;
+      for (uint32_t j = 0; j < skip; j++)
+        sp[(31 - j) * 32] = 0;
+      if (!zero) {
+        br.bp += skip;
+        st.bits -= skip;
+      }
+      st.k = P - (int)skip;
+    }
     if constexpr (P == 64 && N == 64) {
       decode_planes_lockstep<N>(br, kmin, 32, 32, st, sp);
       from_planes_half<1, UInt, N>(u, sp, st.lowest);

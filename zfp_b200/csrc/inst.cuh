@@ -85,10 +85,9 @@ cudaError_t run_encode(const EncodeArgs& a)
   if constexpr (OUT == 0)
     if (a.staged && a.prm.maxbits <= kStagedMaxBits && a.b0 == 0 && a.b1 == a.g.nblocks)
       return run_encode_staged<TYPE, DIMS, REV>(a);
-  // (measured at 1024^3 / 512^3: reversible int32, whose planes below the common precision are dense
-  // noise from the first coded plane on, is the one case where the general kernel's per-plane run
-  // loop beats the lockstep coder's per-item fallback; float, double and int64 are faster here)
-  if constexpr (OUT == 2 && (!REV || TYPE != T_INT32))
+  // variable rate, reversible included (with the empty-plane shortcut the lockstep kernels match or
+  // beat the general kernel's per-plane run loop for every type; measured at 1024^3 / 512^3)
+  if constexpr (OUT == 2)
     if (a.staged)
       return run_encode_var<TYPE, DIMS, REV>(a);
   auto kernel = encode_kernel<TYPE, DIMS, OUT, REV>;
@@ -126,7 +125,7 @@ cudaError_t run_decode(const DecodeArgs& a)
   if constexpr (OFFS == 0)
     if (a.staged && a.prm.maxbits <= kStagedMaxBits && (a.prm.maxbits & 63) == 0 && (a.start_bit & 63) == 0)
       return run_decode_staged<TYPE, DIMS, REV>(a);
-  if constexpr (OFFS == 1 && (!REV || TYPE != T_INT32))
+  if constexpr (OFFS == 1)
     if (a.staged && a.lengths)
       return run_decode_var<TYPE, DIMS, REV>(a);
   auto kernel = decode_kernel<TYPE, DIMS, OFFS, REV>;
