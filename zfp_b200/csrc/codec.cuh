@@ -194,6 +194,7 @@ struct ColWriter {
   __device__ __forceinline__ void append32(uint32_t v, uint32_t len)  // v < 2^len, len <= 32
   {
     const uint32_t sh = bp & 31, w = word_addr();
+    // (shift + OR + funnel shift; forming a0:a1 with one IMAD.WIDE on the idle FMA pipe measured slower)
     const uint32_t a0 = acc | (v << sh);
     const uint32_t a1 = __funnelshift_l(v, 0, sh);
     asm volatile("st.shared.u32 [%0], %1;\n\tst.shared.u32 [%0+128], %2;" ::"r"(w), "r"(a0), "r"(a1) : "memory");
@@ -717,7 +718,7 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
     r = shr32c(x, n);
     verb = x ^ shl32c(r, n);
   }
-  const R y = done ? (R)0 : r;
+  const R y = r;  // finished lanes: T is forced empty below (has / slow are gated), no selects here
   const bool test = !done && n < N;
   const uint32_t y32 = (uint32_t)y;
   const uint32_t c = (uint32_t)__popc(y32);
@@ -726,7 +727,7 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
   const uint32_t r1 = y32 & (y32 - 1), r2 = r1 & (r1 - 1), r3 = r2 & (r2 - 1), r4 = r3 & (r3 - 1);
   bool slow = false;
   if constexpr (N > 32)
-    slow = (uint32_t)((uint64_t)y >> 32) != 0 || msb + (int)c + 2 > 32;
+    slow = !done && ((uint32_t)((uint64_t)y >> 32) != 0 || msb + (int)c + 2 > 32);
   if constexpr (N > 32)
     bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
   else
@@ -735,13 +736,13 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
   uint32_t yp = y32 + r1 + 2 * r2 + 4 * r3;
   // one vote on the common path: more than four new coefficients, or a T that does not fit 32 bits
   bool fast = true;
-  if (__any_sync(FULL, slow || r4 != 0)) {
+  if (__any_sync(FULL, slow || (!done && r4 != 0))) {
     const uint32_t r5 = r4 & (r4 - 1), r6 = r5 & (r5 - 1), r7 = r6 & (r6 - 1), r8 = r7 & (r7 - 1);
     yp += 8 * r4 + 16 * r5 + 32 * r6 + 64 * r7;
-    fast = !__any_sync(FULL, slow || r8 != 0);
+    fast = !__any_sync(FULL, slow || (!done && r8 != 0));
   }
   if (fast) {
-    const bool has = y32 != 0;
+    const bool has = !done && y32 != 0;
     const uint32_t top = n + (uint32_t)(msb + 1);    // coefficients settled after this plane
     const uint32_t last = (has && top == N) ? 1u : 0u;
     const uint32_t keep = (uint32_t)msb + c - last;   // bits + flags, minus the closing flag (and the implied pair)
