@@ -163,23 +163,39 @@ static bool make_geom(const zfp_b200_desc* d, const void* data, Geom* g)
   return true;
 }
 
+// bits a block spends before its coefficients: exponent / reversible-mode prefix and precision
+static uint32_t block_header_bits(const zfp_b200_desc* d)
+{
+  const bool reversible = d->minexp < kMinExp;
+  switch (d->type) {
+    case T_INT32: return reversible ? 5 : 0;
+    case T_INT64: return reversible ? 6 : 0;
+    case T_FLOAT: return reversible ? 15 : 9;
+    default: return reversible ? 19 : 12;
+  }
+}
+
+// Besides the reference's own checks (src/zfp.c:813-824): a maxbits below the block header is refused.
+// Upstream accepts it through zfp_stream_set_params, but then writes the whole header anyway and
+// hands the coefficient coder the wrapped-around budget `maxbits - bits` (src/template/encodef.c:77-82),
+// i.e. unbounded blocks that overrun the size zfp_stream_maximum_size promises the caller
+// (src/zfp.c:711-742).  The rate setter never produces such parameters (src/zfp.c:760-784).
 static bool check_params(const zfp_b200_desc* d)
 {
-  return d->minbits <= d->maxbits && d->maxprec >= 1 && d->maxprec <= 64 && d->maxbits >= 1;
+  if (!(d->minbits <= d->maxbits && d->maxprec >= 1 && d->maxprec <= 64 && d->maxbits >= 1))
+    return false;
+  if (d->maxbits < block_header_bits(d)) {
+    g_error = "maxbits is smaller than the block header: parameters outside zfp_stream_maximum_size's contract";
+    return false;
+  }
+  return true;
 }
 
 // worst-case coded size of one block (the per-block term of zfp_stream_maximum_size, src/zfp.c:711-742)
 static uint32_t block_capacity_bits(const zfp_b200_desc* d)
 {
-  const bool reversible = d->minexp < kMinExp;
   const uint32_t values = 1u << (2 * d->dims), prec = (uint32_t)(8 * scalar_bytes(d->type));
-  uint32_t bits = 0;
-  switch (d->type) {
-    case T_INT32: bits = reversible ? 5 : 0; break;
-    case T_INT64: bits = reversible ? 6 : 0; break;
-    case T_FLOAT: bits = reversible ? 15 : 9; break;
-    default: bits = reversible ? 19 : 12; break;
-  }
+  uint32_t bits = block_header_bits(d);
   bits += values - 1 + values * (d->maxprec < prec ? d->maxprec : prec);
   if (bits > d->maxbits) bits = d->maxbits;
   if (bits < d->minbits) bits = d->minbits;
@@ -263,10 +279,14 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
                                uint64* end_bit, zfp_b200_index* index, void* cuda_stream)
 {
   Geom g;
-  if (!make_geom(d, d_data, &g) || !check_params(d) || !d_data || !d_words) {
+  if (!make_geom(d, d_data, &g) || !d_data || !d_words) {
     g_error = "zfp_b200_encode: invalid descriptor";
     return ZFP_B200_EINVAL;
   }
+  g_error = "zfp_b200_encode: invalid compression parameters";
+  if (!check_params(d))
+    return ZFP_B200_EINVAL;
+  g_error.clear();
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
   const int type = d->type;
@@ -353,10 +373,14 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
                         const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole)
 {
   Geom g;
-  if (!make_geom(d, d_data, &g) || !check_params(d) || !d_data || !d_words) {
+  if (!make_geom(d, d_data, &g) || !d_data || !d_words) {
     g_error = "zfp_b200_decode: invalid descriptor";
     return ZFP_B200_EINVAL;
   }
+  g_error = "zfp_b200_decode: invalid compression parameters";
+  if (!check_params(d))
+    return ZFP_B200_EINVAL;
+  g_error.clear();
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
   int rc;

@@ -1245,6 +1245,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   if constexpr (is_lockstep<Writer>::value) {
     // plane-lockstep coder (fixed rate, column writer); two-phase like the staged path below
     const uint32_t budget = prm.maxbits - bits, start = bw.tell();
+    const uint32_t limit = start + budget < start ? 0xffffffffu : start + budget;  // write position where the budget ends
     const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
     LockState st = { 0, P, !coded };
     if constexpr (REV) {
@@ -1270,31 +1271,31 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
       // undivided half, blocks that go a few planes further (rate 8) with a 16-plane window.
       if (st.k > 32) {
         to_planes_half<1, UInt, N>(u, sp);
-        encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp);
       }
 #pragma unroll 1
       for (int w = 1; w >= 0; w--) {
-        if (!__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < start + budget))
+        if (!__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < limit))
           break;
         if (st.k <= 16 * w)
           continue;
         to_planes_window<0>(u, sp, (uint32_t)w);
-        encode_planes_lockstep<N>(bw, start + budget, kmin, 16 * w, 16 * w, st, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 16 * w, 16 * w, st, sp);
       }
     }
     else if constexpr (P == 64) {
       if (st.k > 32) {
         to_planes_half<1, UInt, N>(u, sp);
-        encode_planes_lockstep<N>(bw, start + budget, kmin, 32, 32, st, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp);
       }
-      if (__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < start + budget)) {
+      if (__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < limit)) {
         to_planes_half<0, UInt, N>(u, sp);
-        encode_planes_lockstep<N>(bw, start + budget, kmin, 0, 0, st, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp);
       }
     }
     else {
       to_planes_half<0, UInt, N>(u, sp);
-      encode_planes_lockstep<N>(bw, start + budget, kmin, 0, 0, st, sp);
+      encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp);
     }
     const uint32_t used = bw.tell() - start;
     bits += used < budget ? used : budget;
