@@ -70,11 +70,12 @@ template <int TYPE, int DIMS, bool REV>
 cudaError_t run_decode_var(const DecodeArgs& a)
 {
   auto kernel = decode_var_kernel<TYPE, DIMS, REV>;
-  constexpr size_t smem = var_smem_bytes<TYPE, DIMS>();
+  constexpr int threads = DecCfg<TYPE>::threads;
+  constexpr size_t smem = var_smem_bytes<TYPE, DIMS>() / (kThreads / 32) * (threads / 32);
   cudaError_t e = allow_smem(kernel, smem);
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;
-  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+  const uint64_t ctas = (a.b1 - a.b0 + threads - 1) / threads;
+  kernel<<<(unsigned)ctas, threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<const uint32_t*>(a.in), a.offsets, a.lengths, a.b0, a.b1);
   return cudaGetLastError();
 }

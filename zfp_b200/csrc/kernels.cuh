@@ -368,7 +368,7 @@ encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g
 }
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
+__global__ void __launch_bounds__(DecCfg<TYPE>::threads, DecCfg<TYPE>::min_ctas(REV))
 decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm, const uint32_t* __restrict__ in,
                   const uint64_t* __restrict__ offsets, const uint16_t* __restrict__ lengths, uint64_t block0, uint64_t block1)
 {
@@ -381,7 +381,7 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
   uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
 
-  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;
   const uint64_t b = valid ? b_raw : block1 - 1;
   const uint64_t off = offsets[b];
