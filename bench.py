@@ -275,22 +275,34 @@ def run_ours(args):
     # ---- end to end through the public C API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     try:
-        hx = torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True)
-        hx.copy_(x)
-        hy = torch.empty((nz, ny, nx), dtype=torch.float64, pin_memory=True)
-        hw = torch.zeros(words.numel(), dtype=torch.int64, pin_memory=True)
+        # pinned host buffers: field in, field out, stream.  All ranks of the node pin at once, so the
+        # slab used for this leg is cut down (whole block layers) if the node's free memory is short.
+        ez = nz
+        try:
+            import psutil
+            budget = 0.5 * psutil.virtual_memory().available / max(1, world)
+            per_layer = (2 * 8 + RATE / 8.0) * ny * nx
+            ez = int(min(nz, max(64, (budget / per_layer) // 4 * 4)))
+        except Exception:
+            pass
+        e_raw = ez * ny * nx * 8
+        e_comp = comp_bytes * ez // nz
+        hx = torch.empty((ez, ny, nx), dtype=torch.float64, pin_memory=True)
+        hx.copy_(x[:ez])
+        hy = torch.empty((ez, ny, nx), dtype=torch.float64, pin_memory=True)
+        hw = torch.zeros(words.numel() * ez // nz + 64, dtype=torch.int64, pin_memory=True)
         L = zb.load_library()
         from zfp_b200.api import Stream, _make_field
         s = Stream(hw.data_ptr(), hw.numel() * 8, mode, 4, 3)
-        fin = _make_field(L, hx.data_ptr(), 4, (nz, ny, nx), None)
-        fout = _make_field(L, hy.data_ptr(), 4, (nz, ny, nx), None)
+        fin = _make_field(L, hx.data_ptr(), 4, (ez, ny, nx), None)
+        fout = _make_field(L, hy.data_ptr(), 4, (ez, ny, nx), None)
 
         def e2e_step():
             L.zfp_stream_rewind(s.z)
             nb = L.zfp_compress(s.z, fin)       # H2D field, kernels, D2H stream
             L.zfp_stream_rewind(s.z)
             nb2 = L.zfp_decompress(s.z, fout)   # H2D stream, kernels, D2H field
-            assert nb == nb2 == comp_bytes, (nb, nb2, comp_bytes)
+            assert nb == nb2 == e_comp, (nb, nb2, e_comp)
 
         e2e_steps = max(1, min(args.steps, 3))
         e2e_step()
@@ -302,10 +314,11 @@ def run_ours(args):
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": 2 * raw_bytes * world / (float(dt.item()) / e2e_steps) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": raw_bytes + comp_bytes, "d2h_bytes_per_step": raw_bytes + comp_bytes,
-               "steps": e2e_steps, "note": "zfp_compress/zfp_decompress on pinned host field + host stream buffer"}
-        same = bool(torch.equal(hy, y.cpu()))
+        e2e = {"value": 2 * e_raw * world / (float(dt.item()) / e2e_steps) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": e_raw + e_comp, "d2h_bytes_per_step": e_raw + e_comp,
+               "steps": e2e_steps, "note": "zfp_compress/zfp_decompress on pinned host field + host stream buffer"
+                                            + ("" if ez == nz else "; first %d of %d layers per rank (host memory)" % (ez, nz))}
+        same = bool(torch.equal(hy, y[:ez].cpu()))
         e2e["matches_device_path"] = same
         L.zfp_field_free(fin)
         L.zfp_field_free(fout)
