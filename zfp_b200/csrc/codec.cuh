@@ -7,8 +7,12 @@
 //   * bit planes are formed by an in-register 32x32 bit-matrix transpose (5 butterfly stages),
 //     not by per-bit loops, and parked in shared memory as [plane][lane] so that every lane's
 //     accesses are conflict free;
-//   * the inherently sequential embedded coder then walks the planes of its block with
-//     popc/ctz arithmetic ("plane strings": n verbatim bits, then group-tested unary runs).
+//   * the embedded coder walks the planes with the whole warp in lockstep ("plane strings": n
+//     verbatim bits, then the group-tested part T of the plane); per plane a lane builds / parses T
+//     with bit-parallel arithmetic instead of a loop over its items (encode_plane_lockstep,
+//     decode_plane_lockstep), falling back to an exact per-item loop where that cannot be proven
+//     right.  The general kernels (odd rates, stream offsets) use the plain per-run loops
+//     (encode_planes / decode_planes).
 //
 // Reference semantics reproduced (paths in the reference tree):
 //   gather/pad      src/template/encode{1,2,3}.c, encode.c:8-27
@@ -1154,7 +1158,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   constexpr bool reversible = REV;  // prm.minexp < ZFP_MIN_EXP, resolved by the launcher
   uint32_t bits = 0, maxprec = prm.maxprec;
   // A block that codes as a single '0' bit skips the coefficient stage by flag, not by an early
-  // return: in the staged path all 32 lanes of the warp must reach the two-phase vote below.
+  // return: in the lockstep kernels all 32 lanes of the warp must reach the warp votes below.
   bool coded = true, pad = true;
   Int q[N];
 
@@ -1243,7 +1247,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     maxprec = prec;
   }
   if constexpr (is_lockstep<Writer>::value) {
-    // plane-lockstep coder (fixed rate, column writer); two-phase like the staged path below
+    // plane-lockstep coder (column writer), planes made resident progressively
     const uint32_t budget = prm.maxbits - bits, start = bw.tell();
     const uint32_t limit = start + budget < start ? 0xffffffffu : start + budget;  // write position where the budget ends
     const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;

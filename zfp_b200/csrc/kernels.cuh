@@ -216,7 +216,7 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #define ZB_MINBLOCKS64 5  // launch-bounds hint for the 64-bit staged kernels; 5 measured best of {4,5,6,8} on B200
 #endif
 constexpr int kStageSlack = 10;   // words of overshoot room: a plane may exceed the budget by < 200 bits and an append stores two words ahead
-constexpr int kStagedPlanes = 32;  // planes resident per phase in the staged kernels (two-phase for 64-bit types)
+constexpr int kStagedPlanes = 32;  // plane words resident at a time in the lockstep kernels (a 32-plane half or a 16-plane window)
 
 template <int TYPE, int DIMS, bool REV>
 __global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
@@ -329,7 +329,7 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   }
 }
 
-// Variable rate, fast path.  Encode: same staged coder, but the block's words leave for its
+// Variable rate, fast path.  Encode: same lockstep coder, but the block's words leave for its
 // scratch slot (the column is a kVarStageWords-word window that is drained at plane boundaries when
 // it runs low) and the coded length is recorded; a scan + compaction pass then places the blocks.
 // Decode: the block starts at an arbitrary bit offset (from the index scan); a window of its words
