@@ -26,6 +26,24 @@ inline cudaError_t allow_smem(K kernel, size_t bytes)
   return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
 
+// the same, remembering per kernel instance AND per device what was already granted (the attribute is
+// per device: a process that drives several GPUs must set it on each)
+template <class K>
+inline cudaError_t allow_smem_cached(K kernel, size_t bytes, size_t (&granted)[64])
+{
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return allow_smem(kernel, bytes);
+  if (bytes > granted[dev]) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    granted[dev] = bytes;
+  }
+  return cudaSuccess;
+}
+
 
 template <int TYPE, int DIMS, bool REV>
 cudaError_t run_encode_staged(const EncodeArgs& a)
@@ -34,12 +52,9 @@ cudaError_t run_encode_staged(const EncodeArgs& a)
   auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
   const size_t smem = (size_t)(kThreads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4);
-  static size_t allowed = 0;  // per kernel instance
-  if (smem > 48 * 1024 && smem > allowed) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    allowed = smem;
-  }
+  static size_t granted[64] = { 0 };  // per kernel instance
+  cudaError_t e = allow_smem_cached(kernel, smem, granted);
+  if (e != cudaSuccess) return e;
   const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
   kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<uint64_t*>(a.out), a.start_bit);
@@ -108,12 +123,9 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
   const size_t smem = (size_t)(DecCfg<TYPE>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4);
-  static size_t allowed = 0;
-  if (smem > 48 * 1024 && smem > allowed) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    allowed = smem;
-  }
+  static size_t granted[64] = { 0 };  // per kernel instance
+  cudaError_t e = allow_smem_cached(kernel, smem, granted);
+  if (e != cudaSuccess) return e;
   const uint64_t ctas = (a.b1 - a.b0 + DecCfg<TYPE>::threads - 1) / DecCfg<TYPE>::threads;
   kernel<<<(unsigned)ctas, DecCfg<TYPE>::threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<const uint64_t*>(a.in), a.start_bit, a.b0, a.b1);
