@@ -315,6 +315,29 @@ def test_random_access_block_range_decode(zb, dtype, shape):
             assert bool((out[~inside] == sentinel).all()), (mode, b0, b1)
 
 
+def test_random_access_box_decode(zb):
+    """decompress_box: the blocks intersecting a coordinate box, nothing else."""
+    import torch
+    for dtype, shape, lo, hi in ((np.float64, (40, 44, 52), (5, 8, 17), (22, 9, 40)), (np.float32, (70, 90), (0, 33), (70, 34)),
+                                 (np.float64, (9, 12, 8, 10), (4, 0, 3, 2), (9, 5, 8, 7))):
+        a = analytic_field(shape, dtype)
+        x = torch.from_numpy(a).cuda()
+        for mode in ({"rate": 6}, {"precision": 24}):
+            c = zb.compress(x, **mode)
+            full = zb.decompress(c)
+            out = torch.full_like(full, 55)
+            zb.decompress_box(c, lo, hi, out)
+            inside = torch.ones(shape, dtype=torch.bool, device="cuda")
+            for ax, (l, h) in enumerate(zip(lo, hi)):
+                coord = torch.arange(shape[ax], device="cuda")
+                keep = (coord >= (l // 4) * 4) & (coord < ((h + 3) // 4) * 4)
+                view = [1] * len(shape)
+                view[ax] = shape[ax]
+                inside &= keep.reshape(view)
+            assert torch.equal(out[inside], full[inside]), (shape, mode)
+            assert bool((out[~inside] == 55).all()), (shape, mode)
+
+
 def test_reference_cli_on_our_backend_c1(tmp_path):
     """BASELINE.json configs[0]: 3-D double 256^3, fixed rate 8, through the reference's own `zfp`
     command-line tool (utils/zfp.c, unmodified).  The tool linked against the drop-in library and run

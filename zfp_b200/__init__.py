@@ -3,6 +3,6 @@
 The package holds the CUDA kernels + C-ABI library (csrc/ -> lib/libzfp_b200.so) and a thin
 ctypes mirror of the reference's host interface (api.py).  See DESIGN.md and INTEGRATION.md.
 """
-from .api import (Compressed, Stream, compress, compress_numpy, decompress, decompress_blocks, decompress_numpy,  # noqa: F401
+from .api import (Compressed, Stream, compress, compress_numpy, decompress, decompress_blocks, decompress_box, decompress_numpy,  # noqa: F401
                   last_error, launch_count, load_library, max_stream_words)
 from .build import build_library  # noqa: F401

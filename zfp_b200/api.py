@@ -342,6 +342,32 @@ def decompress_blocks(c, block0, block1, out):
     return out
 
 
+def decompress_box(c, lo, hi, out):
+    """Random access by coordinates: decode every block that intersects the box lo <= index < hi
+    (one (lo, hi) pair per array dimension, slowest first, like the tensor's shape) into `out`.
+    Blocks are decoded whole, so values of `out` up to 3 positions outside the box along each
+    dimension are written too.  One block-range launch per row of blocks along the fastest dimension."""
+    shape = tuple(out.shape)
+    dims = len(shape)
+    if len(lo) != dims or len(hi) != dims:
+        raise ValueError("lo / hi need one entry per dimension")
+    nb = [(n + 3) // 4 for n in shape]                      # blocks per dimension, slowest first
+    b_lo = [max(0, int(l)) // 4 for l in lo]
+    b_hi = [min((min(int(h), n) + 3) // 4, m) for h, n, m in zip(hi, shape, nb)]
+    if any(a >= b for a, b in zip(b_lo, b_hi)):
+        return out
+    # stream order: x (last dimension) fastest
+    outer = [range(a, b) for a, b in zip(b_lo[:-1], b_hi[:-1])]
+    import itertools
+    for idx in itertools.product(*outer):
+        base = 0
+        for i, m in zip(idx, nb[:-1]):
+            base = base * m + i
+        base *= nb[-1]
+        decompress_blocks(c, base + b_lo[-1], base + b_hi[-1], out)
+    return out
+
+
 # ---- host arrays (numpy), same calls with host pointers: the backend stages through the device ----
 def compress_numpy(a, start_bit=0, prefix_words=None, want_index=False, **mode):
     """zfpy.compress_numpy analogue without header: returns (uint64 words, nbytes[, block lengths])."""
