@@ -733,9 +733,7 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
   if constexpr (N > 32)
     slow = !done && ((uint32_t)((uint64_t)y >> 32) != 0 || msb + (int)c + 2 > 32);
   if constexpr (N > 32)
-    bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);
-  else
-    bw.append32((uint32_t)verb, n);
+    bw.append64((uint32_t)verb, (uint32_t)((uint64_t)verb >> 32), n);  // (blocks of <= 32 values: appended with T below)
   // every one-bit moved up by its rank: b0 + 2 b1 + 4 b2 + 8 b3 + ... = y + r1 + 2 r2 + 4 r3 + ...
   uint32_t yp = y32 + r1 + 2 * r2 + 4 * r3;
   // one vote on the common path: more than four new coefficients, or a T that does not fit 32 bits
@@ -754,23 +752,34 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
     const uint32_t tval = has ? (1u | (e << 1)) : 0u;
     const uint32_t tlen = has ? keep + 2 - last : (test ? 1u : 0u);
     pos = has ? top : pos;
-    bw.append32(tval, tlen);
-  }
-  else if (test) {
-    R rr = y;
-    uint32_t p = n;
-    while (rr) {
-      const uint32_t z = ctz_any<R>(rr);
-      const uint32_t p1 = p + z + 1;
-      const uint64_t ex = p1 < N ? 1u : 0u;           // the one-bit is implied on the last coefficient
-      const uint64_t v = 1ull | shl64c(ex, z + 1);    // '1', z zeros, '1'
-      bw.append64((uint32_t)v, (uint32_t)(v >> 32), z + 1 + (uint32_t)ex);
-      rr = (R)shr64c((uint64_t)rr, z + 1);
-      p = p1;
+    if constexpr (N > 32)
+      bw.append32(tval, tlen);
+    else if (!__any_sync(FULL, n + tlen > 32))
+      bw.append32((uint32_t)verb | shl32c(tval, n), n + tlen);  // small blocks: the whole plane string in one append
+    else {
+      bw.append32((uint32_t)verb, n);
+      bw.append32(tval, tlen);
     }
-    if (p < N)
-      bw.append32(0, 1);  // closing (or only) group test
-    pos = p;
+  }
+  else {
+    if constexpr (N <= 32)
+      bw.append32((uint32_t)verb, n);
+    if (test) {
+      R rr = y;
+      uint32_t p = n;
+      while (rr) {
+        const uint32_t z = ctz_any<R>(rr);
+        const uint32_t p1 = p + z + 1;
+        const uint64_t ex = p1 < N ? 1u : 0u;           // the one-bit is implied on the last coefficient
+        const uint64_t v = 1ull | shl64c(ex, z + 1);    // '1', z zeros, '1'
+        bw.append64((uint32_t)v, (uint32_t)(v >> 32), z + 1 + (uint32_t)ex);
+        rr = (R)shr64c((uint64_t)rr, z + 1);
+        p = p1;
+      }
+      if (p < N)
+        bw.append32(0, 1);  // closing (or only) group test
+      pos = p;
+    }
   }
 }
 
@@ -892,7 +901,16 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   rec.dst = plane;
   rec.store = !done;
   lowest = done ? lowest : k;
-  const uint32_t w = br.peek32(tp);
+  uint32_t w;
+  R verb_small = 0;  // blocks of <= 32 values: verbatim bits and T come from one 64-bit look (m <= 32 - so no deferred fetch)
+  if constexpr (N > 32)
+    w = br.peek32(tp);
+  else {
+    uint32_t lo, hi;
+    br.peek64(br.bp, lo, hi);
+    verb_small = lo ^ shl32c(shr32c(lo, m), m);
+    w = m < 32 ? __funnelshift_r(lo, hi, m) : hi;
+  }
   const uint32_t left = bits - m;                        // budget at T (m <= bits)
   const bool test = !done && n < N && left != 0;
   // parse T: W' = virtual data bit, then the stream
@@ -911,7 +929,8 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   const uint32_t d0 = d >> 2, d1 = d0 & (d0 - 1), d2 = d1 & (d1 - 1), d3 = d2 & (d2 - 1), d4 = d3 & (d3 - 1);
   bool slow = test && (term == 0 || tpos > left || (c != 0 && ntop > N - 1));
   uint32_t y = d0 - (d1 >> 1) - (d2 >> 2) - (d3 >> 3);
-  finish_plane<N>(br, prev);  // the previous plane's leftover work: independent of everything above
+  if constexpr (N > 32)
+    finish_plane<N>(br, prev);  // the previous plane's leftover work: independent of everything above
   // one vote on the common path: more than four new coefficients, or something the shortcut cannot prove
   bool fast = true;
   if (__any_sync(FULL, slow || d4 != 0)) {
@@ -966,6 +985,11 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
     bits = b;
     br.bp = p;
     n = nn;
+  }
+  if constexpr (N <= 32) {
+    if (rec.store)
+      *rec.dst = verb_small | rec.ybits;
+    rec.store = false;
   }
 }
 
