@@ -50,13 +50,14 @@ cudaError_t run_encode_staged(const EncodeArgs& a)
 {
   constexpr int N = 1 << (2 * DIMS);
   auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
-  const size_t smem = (size_t)(kThreads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
-                                                 ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4);
+  constexpr int threads = EncCfg<TYPE>::threads;
+  const size_t smem = (size_t)(threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
+                                                ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4);
   static size_t granted[64] = { 0 };  // per kernel instance
   cudaError_t e = allow_smem_cached(kernel, smem, granted);
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (a.g.nblocks + kThreads - 1) / kThreads;
-  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+  const uint64_t ctas = (a.g.nblocks + threads - 1) / threads;
+  kernel<<<(unsigned)ctas, threads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<uint64_t*>(a.out), a.start_bit);
   return cudaGetLastError();
 }
@@ -72,11 +73,12 @@ template <int TYPE, int DIMS, bool REV>
 cudaError_t run_encode_var(const EncodeArgs& a)
 {
   auto kernel = encode_var_kernel<TYPE, DIMS, REV>;
-  constexpr size_t smem = var_smem_bytes<TYPE, DIMS>();
+  constexpr int threads = EncCfg<TYPE>::threads;
+  constexpr size_t smem = var_smem_bytes<TYPE, DIMS>() / (kThreads / 32) * (threads / 32);
   cudaError_t e = allow_smem(kernel, smem);
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;
-  kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+  const uint64_t ctas = (a.b1 - a.b0 + threads - 1) / threads;
+  kernel<<<(unsigned)ctas, threads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<uint32_t*>(a.out), a.slot_words * 2, a.lengths, a.b0, a.b1);
   return cudaGetLastError();
 }

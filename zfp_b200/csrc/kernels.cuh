@@ -215,11 +215,25 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_MINBLOCKS64
 #define ZB_MINBLOCKS64 5  // launch-bounds hint for the 64-bit staged kernels; 5 measured best of {4,5,6,8} on B200
 #endif
+// encode_staged_kernel / encode_var_kernel: CTA size and CTAs per SM by plane width.  The 64-bit kernels
+// measured 3-4 % faster with 4 warps per CTA (512^3 fp64 rate 8: 0.605 -> 0.581 ms; 192 threads and
+// CTA-wide rendezvous points gave nothing more); the 32-bit ones keep 2 warps.
+#ifndef ZB_ENC64_THREADS
+#define ZB_ENC64_THREADS 128
+#endif
+template <int TYPE> struct EncCfg {
+  static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_ENC64_THREADS : kThreads;
+  static constexpr int min_ctas(bool rev)
+  {
+    // 64-bit: 384 threads per SM (<= 168 registers per thread), as with 6 CTAs of 64 threads
+    return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? 6 : 9);
+  }
+};
 constexpr int kStageSlack = 10;   // words of overshoot room: a plane may exceed the budget by < 200 bits and an append stores two words ahead
 constexpr int kStagedPlanes = 32;  // plane words resident at a time in the lockstep kernels (a 32-plane half or a 16-plane window)
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
+__global__ void __launch_bounds__(EncCfg<TYPE>::threads, EncCfg<TYPE>::min_ctas(REV))
 encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      uint64_t* __restrict__ out, uint64_t start_bit)
 {
@@ -235,7 +249,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 
   // no early exit: lanes past the end redo the last block and discard it, so that warp-wide votes
   // inside encode_block always see 32 lanes
-  const uint64_t b_raw = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint64_t b_raw = (uint64_t)blockIdx.x * EncCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < g.nblocks;
   const uint64_t b = valid ? b_raw : g.nblocks - 1;
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
@@ -337,7 +351,7 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
 constexpr int kVarStageWords = 64;  // 2048 bits: more than almost every variable-rate block
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(kThreads, Traits<TYPE>::P == 32 ? (REV ? 6 : 9) : (REV ? 4 : ZB_MINBLOCKS64))
+__global__ void __launch_bounds__(EncCfg<TYPE>::threads, EncCfg<TYPE>::min_ctas(REV))
 encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                   uint32_t* __restrict__ slots, uint32_t slot_words32, uint16_t* __restrict__ lengths,
                   uint64_t block0, uint64_t block1)
@@ -351,7 +365,7 @@ encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
   uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
 
-  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * EncCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;
   const uint64_t b = valid ? b_raw : block1 - 1;
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
