@@ -24,7 +24,7 @@ def _cases(seed, count):
     kinds = ["smooth", "noise", "sparse", "tiny", "huge", "special"]
     for _ in range(count):
         dims = int(rng.integers(1, 5))
-        hi = {1: 3000, 2: 70, 3: 24, 4: 10}[dims]
+        hi = {1: 3000, 2: 70, 3: 24, 4: 10}[dims] * (3 if rng.integers(0, 8) == 0 else 1)   # now and then a larger array
         shape = tuple(int(rng.integers(1, hi)) for _ in range(dims))
         dtype = dtypes[int(rng.integers(0, 4))]
         kind = kinds[int(rng.integers(0, len(kinds)))]

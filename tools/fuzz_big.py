@@ -5,7 +5,9 @@ from test_gpu_fuzz import _cases
 from helpers import make_field
 from oracle.oracle import Port
 P=Port(); bad=[]; n=0
-for seed in range(1000, 1040):
+import os
+lo = int(os.environ.get('FUZZ_LO', '1000')); hi = int(os.environ.get('FUZZ_HI', '1040'))
+for seed in range(lo, hi):
     for shape, dtype, kind, mode, fseed in _cases(seed, 70):
         a = make_field(shape, dtype, fseed, kind); x = torch.from_numpy(a).cuda()
         try:
