@@ -111,6 +111,8 @@ size_t zfp_b200_capacity(const zfp_b200_desc* desc, uint64 start_bit);
 zfp_b200_index* zfp_b200_index_create(void);
 void zfp_b200_index_destroy(zfp_b200_index* index);
 size_t zfp_b200_index_blocks(const zfp_b200_index* index);
+/* total coded bits of the blocks (sum of the lengths) as recorded by the encode that filled the index; 0 after an import */
+uint64 zfp_b200_index_bits(const zfp_b200_index* index);
 /* serialised form: 16-bit coded length per block, block order = stream order */
 size_t zfp_b200_index_export(const zfp_b200_index* index, uint16_t* host_lengths, size_t capacity);
 int zfp_b200_index_import(zfp_b200_index* index, const uint16_t* host_lengths, size_t blocks);

@@ -89,7 +89,7 @@ _PROTOTYPES = {
     "zfp_b200_bitcopy": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]),
     "zfp_b200_is_fixed_rate": (C.c_int, [C.POINTER(Desc)]), "zfp_b200_blocks": (_sz, [C.POINTER(Desc)]),
     "zfp_b200_capacity": (_sz, [C.POINTER(Desc), C.c_uint64]),
-    "zfp_b200_index_create": (_vp, []), "zfp_b200_index_destroy": (None, [_vp]),
+    "zfp_b200_index_create": (_vp, []), "zfp_b200_index_destroy": (None, [_vp]), "zfp_b200_index_bits": (C.c_uint64, [_vp]),
     "zfp_b200_index_blocks": (_sz, [_vp]), "zfp_b200_index_export": (_sz, [_vp, _vp, _sz]),
     "zfp_b200_index_import": (C.c_int, [_vp, _vp, _sz]),
     "zfp_b200_last_error": (C.c_char_p, []), "zfp_b200_launch_count": (C.c_uint64, []),
@@ -208,6 +208,12 @@ class Stream:
             self.close()
         except Exception:
             pass
+
+    def index_bits(self):
+        """Total coded bits of the last variable-rate compress on this stream (no copy of the index)."""
+        p = self.L.zfp_stream_cuda_params(self.z)
+        ix = p.contents.index if p else None
+        return int(self.L.zfp_b200_index_bits(ix)) if ix else 0
 
     def index_lengths(self):
         """Per-block coded lengths (numpy uint16) of the last variable-rate compress, or None."""

@@ -94,6 +94,7 @@ struct zfp_b200_index {
   uint16_t* d_lengths = nullptr;
   size_t blocks = 0;
   size_t capacity = 0;
+  uint64_t total_bits = 0;  // sum of the lengths, recorded by the encode that filled the index
 };
 
 extern "C" zfp_b200_index* zfp_b200_index_create(void) { return new (std::nothrow) zfp_b200_index(); }
@@ -119,6 +120,7 @@ static bool index_reserve(zfp_b200_index* ix, size_t blocks)
 }
 
 extern "C" size_t zfp_b200_index_blocks(const zfp_b200_index* ix) { return ix ? ix->blocks : 0; }
+extern "C" uint64 zfp_b200_index_bits(const zfp_b200_index* ix) { return ix ? ix->total_bits : 0; }
 
 extern "C" size_t zfp_b200_index_export(const zfp_b200_index* ix, uint16_t* host, size_t capacity)
 {
@@ -351,6 +353,7 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (end_bit) *end_bit = h_cursor[1];
+  if (index) index->total_bits = h_cursor[1] - start_bit;
   return ZFP_B200_OK;
 }
 

@@ -117,7 +117,7 @@ def compress_slab_cuda(slab, plan, mode, start_bit=0, group=None):
     if api.is_fixed_rate_mode(mode):
         maxbits = api.mode_params(mode, str(slab.dtype), slab.dim())[1]
         return c, plan.blocks * maxbits, fixed_rate_base_bit(plan, maxbits, start_bit), None
-    nbits = int(c.stream.index_lengths().astype(np.int64).sum())
+    nbits = c.stream.index_bits()  # recorded by the encode: no copy of the per-block index to the host
     base, lengths = slab_base_bits(nbits, start_bit, group)
     return c, nbits, base, lengths
 
