@@ -130,7 +130,7 @@ def test_long_blocks_and_noisy_planes(zb, port, dtype, shape):
 
 
 @pytest.mark.parametrize("dtype,shape,rate", [(np.float32, (262, 256, 256), 8), (np.float64, (70, 512, 500), 4),
-                                              (np.float32, (5000, 4100), 16)])
+                                              (np.float32, (5000, 4100), 16), (np.float64, (9000001,), 8)])
 def test_host_buffers_slab_pipeline(zb, dtype, shape, rate):
     """Host field + host stream at a fixed rate above the pipelining threshold: the backend cuts the
     array into slabs along the slowest dimension and overlaps H2D / kernels / D2H.  The stream and

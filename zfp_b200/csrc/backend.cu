@@ -540,7 +540,7 @@ struct SlabPlan {
 // decide whether (and how) to pipeline; false = use the monolithic path
 bool plan_slabs(const zfp_b200_desc& d, uint64_t start_bit, size_t esize, SlabPlan* plan)
 {
-  if (d.minbits != d.maxbits || d.dims < 2 || (start_bit & 63)) return false;
+  if (d.minbits != d.maxbits || d.dims < 1 || (start_bit & 63)) return false;
   ptrdiff_t expect = 1;
   for (uint32_t i = 0; i < d.dims; i++) {  // default (contiguous) layout only, implied or spelled out
     if (d.s[i] != 0 && d.s[i] != expect) return false;
