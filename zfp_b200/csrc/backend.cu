@@ -298,8 +298,15 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
   if (d->minbits == d->maxbits) {
     // fixed rate: block b lives at start + b*maxbits, no communication between blocks
     const uint64_t total = g.nblocks * (uint64_t)d->maxbits, end = start_bit + total;
-    if ((start_bit & 63) == 0 && (d->maxbits & 63) == 0)
+    // blocks of whole 64-bit words go out with plain stores from any kernel; blocks of whole 32-bit
+    // words too, from the column kernels (dims <= 3, budget within their staging limit)
+    static const bool staged = getenv("ZFP_B200_NO_STAGED") == nullptr;
+    const bool words32 = (d->maxbits & 31) == 0 && staged && dims <= 3 && d->maxbits <= 4096;
+    if ((start_bit & 63) == 0 && ((d->maxbits & 63) == 0 || words32)) {
+      if (end & 63)  // the stream ends mid-word: the rest of that word reads as zero, as after stream_flush
+        CU(cudaMemsetAsync(static_cast<uint64_t*>(d_words) + (end >> 6), 0, 8, st));
       rc = encode_any(0, type, dims, d_data, g, prm, d_words, start_bit, 0, nullptr, 0, g.nblocks, st);
+    }
     else {
       uint64_t* w = static_cast<uint64_t*>(d_words);
       const uint64_t w0 = (start_bit + 63) >> 6, w1 = (end + 63) >> 6;

@@ -481,6 +481,38 @@ __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
   transpose32_stage<1>(a);
 }
 
+// Small blocks (M = 16 or 4 coefficients): the 32-bit words of the M coefficients form 32/M square
+// M x M bit matrices side by side; transposing each in place (log2 M butterfly stages on M words,
+// the masks are periodic so all matrices go at once) leaves word i = [plane i | plane M+i | ...],
+// M bits each.  A quarter / a sixteenth of the work of padding to a 32x32 matrix.
+template <int J, int M>
+__device__ __forceinline__ void transpose_small_stage(uint32_t (&a)[M])
+{
+  constexpr uint32_t m = J == 8 ? 0x00ff00ffu : J == 4 ? 0x0f0f0f0fu : J == 2 ? 0x33333333u : 0x55555555u;
+#pragma unroll
+  for (int k = 0; k < M; k++)
+    if (!(k & J)) {
+      if (J == 8) {
+        const uint32_t lo = __byte_perm(a[k], a[k + J], 0x6240), hi = __byte_perm(a[k], a[k + J], 0x7351);
+        a[k] = lo;
+        a[k + J] = hi;
+      }
+      else {
+        uint32_t t = ((a[k] >> J) ^ a[k + J]) & m;
+        a[k + J] ^= t;
+        a[k] ^= t << J;
+      }
+    }
+}
+template <int M>
+__device__ __forceinline__ void transpose_small(uint32_t (&a)[M])
+{
+  if constexpr (M >= 16) transpose_small_stage<8, M>(a);
+  if constexpr (M >= 8) transpose_small_stage<4, M>(a);
+  transpose_small_stage<2, M>(a);
+  transpose_small_stage<1, M>(a);
+}
+
 // Plane storage in shared memory: plane k of the calling lane is sp[k * 32] where sp already
 // points at the lane's column (conflict free for 4- and 8-byte words).
 template <int N> struct PlaneWord { using type = uint32_t; };
@@ -548,6 +580,19 @@ __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWo
 template <int H, class UInt, int N>
 __device__ __forceinline__ void to_planes_half(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
 {
+  if constexpr (N == 16 || N == 4) {
+    uint32_t a[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      a[i] = (uint32_t)(u[i] >> (32 * H));
+    transpose_small<N>(a);
+#pragma unroll
+    for (int q = 0; q < 32 / N; q++)
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        sp[(N * q + i) * 32] = (a[i] >> (N * q)) & ((1u << N) - 1);
+    return;
+  }
   constexpr int G = (N + 31) / 32;
   uint32_t a[G][32];
 #pragma unroll
@@ -570,6 +615,24 @@ __device__ __forceinline__ void to_planes_half(const UInt (&u)[N], typename Plan
 template <int H, class UInt, int N>
 __device__ __forceinline__ void from_planes_half(UInt (&u)[N], const typename PlaneWord<N>::type* sp, int kstop)
 {
+  if constexpr (N == 16 || N == 4) {
+    uint32_t a[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      a[i] = 0;
+#pragma unroll
+    for (int q = 0; q < 32 / N; q++)
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        const uint32_t x = (32 * H + N * q + i >= kstop) ? (uint32_t)sp[(N * q + i) * 32] : 0u;
+        a[i] |= x << (N * q);
+      }
+    transpose_small<N>(a);
+#pragma unroll
+    for (int i = 0; i < N; i++)
+      u[i] |= (UInt)((UInt)a[i] << (32 * H));
+    return;
+  }
   constexpr int G = (N + 31) / 32;
   uint32_t a[G][32];
 #pragma unroll

@@ -138,6 +138,8 @@ template <int TYPE, int DIMS, int OFFS, bool REV>
 cudaError_t run_decode(const DecodeArgs& a)
 {
   if constexpr (OFFS == 0)
+    // (blocks of an odd number of 32-bit words would work here too - the encoder takes them - but the general
+    // kernel decodes them faster: 1-D fp64 at 8 bits/value 2.4 ms against 3.1 ms)
     if (a.staged && a.prm.maxbits <= kStagedMaxBits && (a.prm.maxbits & 63) == 0 && (a.start_bit & 63) == 0)
       return run_decode_staged<TYPE, DIMS, REV>(a);
   if constexpr (OFFS == 1)

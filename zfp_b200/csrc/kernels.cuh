@@ -241,7 +241,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   constexpr int N = 1 << (2 * DIMS);
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
-  const uint32_t words = prm.maxbits >> 5;  // 32-bit words per block (even: maxbits % 64 == 0)
+  const uint32_t words = prm.maxbits >> 5;  // 32-bit words per block (maxbits % 32 == 0)
   const uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (words + kStageSlack) * 32 * 4;
   char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
   PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
@@ -262,18 +262,24 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   bw.finish(words);
 
   if (valid) {
-    uint64_t* dst = out + (start_bit >> 6) + b * (uint64_t)(words >> 1);
-    if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(out + (start_bit >> 6)) + b * (uint64_t)words;
+    if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(dst32) & 15) == 0) {
       // 16-byte stores: a block's words are contiguous in the stream
-      uint4* dst4 = reinterpret_cast<uint4*>(dst);
+      uint4* dst4 = reinterpret_cast<uint4*>(dst32);
 #pragma unroll 4
       for (uint32_t w = 0; w < words; w += 4)
         dst4[w >> 2] = make_uint4(stage[w * 32], stage[(w + 1) * 32], stage[(w + 2) * 32], stage[(w + 3) * 32]);
     }
-    else {
+    else if ((words & 1) == 0) {
+      uint64_t* dst = reinterpret_cast<uint64_t*>(dst32);
 #pragma unroll 4
       for (uint32_t w = 0; w < words; w += 2)
         dst[w >> 1] = (uint64_t)stage[w * 32] | ((uint64_t)stage[(w + 1) * 32] << 32);
+    }
+    else {
+      // an odd number of 32-bit words per block (e.g. 1-D at 8 bits/value): word stores, coalesced across lanes
+      for (uint32_t w = 0; w < words; w++)
+        dst32[w] = stage[w * 32];
     }
   }
 }
@@ -309,9 +315,10 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;  // no early exit (warp-wide votes in decode_block)
   const uint64_t b = valid ? b_raw : block1 - 1;
-  const uint64_t* src = in + (start_bit >> 6) + b * (uint64_t)(words >> 1);
-  if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(in + (start_bit >> 6)) + b * (uint64_t)words;
+  const uint64_t* src = reinterpret_cast<const uint64_t*>(src32);
+  if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(src32) & 15) == 0) {
+    const uint4* src4 = reinterpret_cast<const uint4*>(src32);
 #pragma unroll 4
     for (uint32_t w = 0; w < words; w += 4) {
       const uint4 v = __ldg(src4 + (w >> 2));
@@ -321,13 +328,17 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
       stage[(w + 3) * 32] = v.w;
     }
   }
-  else {
+  else if ((words & 1) == 0) {
 #pragma unroll 4
     for (uint32_t w = 0; w < words; w += 2) {
       const uint64_t v = __ldg(src + (w >> 1));
       stage[w * 32] = (uint32_t)v;
       stage[(w + 1) * 32] = (uint32_t)(v >> 32);
     }
+  }
+  else {
+    for (uint32_t w = 0; w < words; w++)
+      stage[w * 32] = __ldg(src32 + w);
   }
 #pragma unroll
   for (int j = 0; j < kReadSlack; j++)
