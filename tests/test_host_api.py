@@ -210,3 +210,43 @@ def test_field_accessors(lib):
     lib.zfp_field_set_stride_3d(f, 2, 10, 60)
     assert lib.zfp_field_is_contiguous(f) == 0 and lib.zfp_field_size_bytes(f) == 8 * (2 * 4 + 10 * 5 + 60 * 6 + 1)
     lib.zfp_field_free(f)
+
+
+def test_headers_are_plain_c_and_a_c_program_links(tmp_path, lib):
+    """The boundary is a C ABI: every header under include/ compiles as C99 and as C++17 with no CUDA or
+    torch in sight, and a C program written against zfp.h (the reference's own include name) links
+    against libzfp_b200.so and can set up a stream without touching the GPU."""
+    import shutil
+    import subprocess
+    from zfp_b200 import build as _build
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    inc = os.path.join(ROOT, "include")
+    for h in ("zfp.h", "zfp_b200.h", "zfp_b200_backend.h"):
+        subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, "-x", "c", os.path.join(inc, h)], check=True)
+        subprocess.run([cxx, "-std=c++17", "-fsyntax-only", "-I", inc, "-x", "c++", os.path.join(inc, h)], check=True)
+    src = tmp_path / "prog.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "zfp.h"
+#include "zfp_b200_backend.h"
+int main(void)
+{
+  double a[64] = { 0 };
+  zfp_field* f = zfp_field_3d(a, zfp_type_double, 4, 4, 4);
+  zfp_stream* z = zfp_stream_open(NULL);
+  double rate = zfp_stream_set_rate(z, 8.0, zfp_type_double, 3, zfp_false);
+  size_t cap = zfp_stream_maximum_size(z, f);
+  int ok = zfp_stream_set_execution(z, zfp_exec_cuda);
+  zfp_b200_desc d = { zfp_type_double, 3, { 4, 4, 4, 0 }, { 0, 0, 0, 0 }, 512, 512, 64, -1074 };
+  printf("%g %zu %d %zu %d\n", rate, cap, ok, zfp_b200_blocks(&d), zfp_b200_is_fixed_rate(&d));
+  zfp_field_free(f);
+  zfp_stream_close(z);
+  return 0;
+}
+''')
+    exe = tmp_path / "prog"
+    libdir = os.path.dirname(_build.LIB)
+    subprocess.run([cc, "-std=c99", "-Wall", "-I", inc, "-o", str(exe), str(src), "-L", libdir, "-lzfp_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out == ["8", "88", "1", "1", "1"], out   # (148 + 512 + 63) & ~63 bits = 704 bits = 88 bytes
