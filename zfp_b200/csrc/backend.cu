@@ -353,7 +353,7 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
     if (rc) return rc;
     zero_new_words<<<148 * 4, 256, 0, st>>>(static_cast<uint64_t*>(d_words), cursor);
     LAUNCHED();
-    compact_blocks<<<(unsigned)((cn + 255) / 256), 256, 0, st>>>(slots, slot_words, lengths + b0, offsets, cn, d_words);
+    compact_blocks<<<(unsigned)((cn * kCompactLanes + 255) / 256), 256, 0, st>>>(slots, slot_words, lengths + b0, offsets, cn, d_words);
     LAUNCHED();
   }
   uint64_t h_cursor[2];

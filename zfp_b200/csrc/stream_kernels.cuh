@@ -146,24 +146,40 @@ __global__ void zero_new_words(uint64_t* __restrict__ words, const uint64_t* __r
 }
 
 // concatenate the coded blocks of a chunk: block b's bits move from its scratch slot to its bit
-// offset in the stream (stream_copy semantics, include/zfp/bitstream.inl:412-424)
+// offset in the stream (stream_copy semantics, include/zfp/bitstream.inl:412-424).  Eight lanes per
+// block, one destination word per lane and step: the slot is read with neighbouring lanes on
+// neighbouring words, words inside the block go out with plain stores and only the (at most two)
+// words shared with the neighbouring blocks are OR-merged into the pre-zeroed destination.
+constexpr int kCompactLanes = 8;
 __global__ void __launch_bounds__(256)
 compact_blocks(const uint64_t* __restrict__ scratch, uint32_t slot_words, const uint16_t* __restrict__ lengths,
                const uint64_t* __restrict__ offsets, uint64_t nblocks, void* __restrict__ out)
 {
-  const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t b = t / kCompactLanes;
   if (b >= nblocks)
     return;
+  const uint32_t lane = (uint32_t)(t % kCompactLanes);
   const uint64_t* src = scratch + b * slot_words;
-  uint32_t len = lengths[b];
-  BitWriter<1> bw;
-  bw.init(out, offsets[b]);
-  for (uint32_t i = 0; len; i++) {
-    uint32_t c = len < 64 ? len : 64;
-    bw.put(src[i] & lowmask64(c), c);
-    len -= c;
+  const uint64_t len = lengths[b], off = offsets[b];
+  uint64_t* dst = static_cast<uint64_t*>(out);
+  const uint64_t w0 = off >> 6, w1 = (off + len + 63) >> 6;  // destination words [w0, w1)
+  for (uint64_t w = w0 + lane; w < w1; w += kCompactLanes) {
+    const uint64_t lo = w * 64 > off ? w * 64 : off;
+    const uint64_t hi = (w + 1) * 64 < off + len ? (w + 1) * 64 : off + len;
+    const uint32_t n = (uint32_t)(hi - lo);       // bits of this block in word w
+    const uint64_t sbit = lo - off;                // first source bit
+    const uint32_t sh = (uint32_t)(sbit & 63);
+    uint64_t v = src[sbit >> 6] >> sh;
+    if (sh && sh + n > 64)
+      v |= src[(sbit >> 6) + 1] << (64 - sh);
+    v &= lowmask64(n);
+    v <<= (uint32_t)(lo & 63);
+    if (n == 64)
+      dst[w] = v;
+    else if (v)
+      atomicOr(reinterpret_cast<unsigned long long*>(dst + w), (unsigned long long)v);
   }
-  bw.flush();
 }
 
 // Bit-granular device copy: dst[dst_bit, dst_bit+nbits) = src[src_bit, src_bit+nbits).  Words of dst
