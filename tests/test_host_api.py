@@ -250,3 +250,30 @@ int main(void)
     subprocess.run([cc, "-std=c99", "-Wall", "-I", inc, "-o", str(exe), str(src), "-L", libdir, "-lzfp_b200", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     assert out == ["8", "88", "1", "1", "1"], out   # (148 + 512 + 63) & ~63 bits = 704 bits = 88 bytes
+
+
+def test_box_block_ranges_against_brute_force():
+    """Host logic of the coordinate-box random access: the block ranges cover exactly the blocks that
+    intersect the box (stream order: last dimension fastest)."""
+    import itertools
+    from zfp_b200.api import box_block_ranges
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        dims = int(rng.integers(1, 5))
+        shape = tuple(int(rng.integers(1, 23)) for _ in range(dims))
+        lo = [int(rng.integers(-2, n + 2)) for n in shape]
+        hi = [int(rng.integers(l, n + 4)) for l, n in zip(lo, shape)]
+        nb = [(n + 3) // 4 for n in shape]
+        want = set()
+        for blk in itertools.product(*[range(m) for m in nb]):
+            hit = all(4 * b < min(h, n) and 4 * b + 4 > max(l, 0) for b, l, h, n in zip(blk, lo, hi, shape))
+            if hit:
+                lin = 0
+                for b, m in zip(blk, nb):
+                    lin = lin * m + b
+                want.add(lin)
+        got = set()
+        for b0, b1 in box_block_ranges(shape, lo, hi):
+            assert 0 <= b0 < b1 <= int(np.prod(nb))
+            got |= set(range(b0, b1))
+        assert got == want, (shape, lo, hi)

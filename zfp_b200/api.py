@@ -348,12 +348,11 @@ def decompress_blocks(c, block0, block1, out):
     return out
 
 
-def decompress_box(c, lo, hi, out):
-    """Random access by coordinates: decode every block that intersects the box lo <= index < hi
-    (one (lo, hi) pair per array dimension, slowest first, like the tensor's shape) into `out`.
-    Blocks are decoded whole, so values of `out` up to 3 positions outside the box along each
-    dimension are written too.  One block-range launch per row of blocks along the fastest dimension."""
-    shape = tuple(out.shape)
+def box_block_ranges(shape, lo, hi):
+    """Block ranges [b0, b1) (stream order, last dimension fastest) of the 4^d blocks that intersect the
+    box lo <= index < hi of an array of this shape: one range per row of blocks along the fastest dimension."""
+    import itertools
+    shape = tuple(int(n) for n in shape)
     dims = len(shape)
     if len(lo) != dims or len(hi) != dims:
         raise ValueError("lo / hi need one entry per dimension")
@@ -361,16 +360,24 @@ def decompress_box(c, lo, hi, out):
     b_lo = [max(0, int(l)) // 4 for l in lo]
     b_hi = [min((min(int(h), n) + 3) // 4, m) for h, n, m in zip(hi, shape, nb)]
     if any(a >= b for a, b in zip(b_lo, b_hi)):
-        return out
-    # stream order: x (last dimension) fastest
-    outer = [range(a, b) for a, b in zip(b_lo[:-1], b_hi[:-1])]
-    import itertools
-    for idx in itertools.product(*outer):
+        return []
+    ranges = []
+    for idx in itertools.product(*[range(a, b) for a, b in zip(b_lo[:-1], b_hi[:-1])]):
         base = 0
         for i, m in zip(idx, nb[:-1]):
             base = base * m + i
         base *= nb[-1]
-        decompress_blocks(c, base + b_lo[-1], base + b_hi[-1], out)
+        ranges.append((base + b_lo[-1], base + b_hi[-1]))
+    return ranges
+
+
+def decompress_box(c, lo, hi, out):
+    """Random access by coordinates: decode every block that intersects the box lo <= index < hi
+    (one (lo, hi) pair per array dimension, slowest first, like the tensor's shape) into `out`.
+    Blocks are decoded whole, so values of `out` up to 3 positions outside the box along each
+    dimension are written too.  One block-range launch per row of blocks along the fastest dimension."""
+    for b0, b1 in box_block_ranges(tuple(out.shape), lo, hi):
+        decompress_blocks(c, b0, b1, out)
     return out
 
 
