@@ -235,7 +235,8 @@ def run_ours(args):
 
     def step(record=None):
         if record: record[0].record()
-        c = zb.compress(x, out=words, async_fixed_rate=True, reuse=prev[0], **mode)
+        # the first call creates the zfp_stream over `words`; later calls rewind and recycle it
+        c = zb.compress(x, reuse=prev[0], **mode) if prev[0] is not None else zb.compress(x, out=words, async_fixed_rate=True, **mode)
         prev[0] = c
         if record: record[1].record()
         zb.decompress(c, out=y)

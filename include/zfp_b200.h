@@ -70,6 +70,20 @@ typedef enum {
   zfp_mode_reversible = 5
 } zfp_mode;
 
+/* compression mode and parameter settings (include/zfp.h:106-119) */
+typedef struct {
+  zfp_mode mode;
+  union {
+    double rate;      /* compressed bits/value (negative for word alignment) */
+    uint precision;   /* uncompressed bits/value */
+    double tolerance; /* absolute error tolerance */
+    struct {
+      uint minbits, maxbits, maxprec;
+      int minexp;
+    } expert;
+  } arg;
+} zfp_config;
+
 typedef enum {
   zfp_type_none = 0,
   zfp_type_int32 = 1,
@@ -201,6 +215,18 @@ zfp_exec_policy zfp_stream_execution(const zfp_stream* zfp);
 zfp_bool zfp_stream_set_execution(zfp_stream* zfp, zfp_exec_policy policy); /* zfp_exec_omp -> zfp_false */
 uint zfp_stream_omp_threads(const zfp_stream* zfp);
 uint zfp_stream_omp_chunk_size(const zfp_stream* zfp);
+/* OpenMP execution lives in the reference library: both return zfp_false and leave the policy alone
+ * (include/zfp.h:322-333; the reference returns zfp_false the same way when built without OpenMP) */
+zfp_bool zfp_stream_set_omp_threads(zfp_stream* zfp, uint threads);
+zfp_bool zfp_stream_set_omp_chunk_size(zfp_stream* zfp, uint chunk_size);
+
+/* ---- mode configurations (include/zfp.h:335-371; src/zfp.c:466-533) -------------------------- */
+zfp_config zfp_config_none(void);
+zfp_config zfp_config_rate(double rate, zfp_bool align);
+zfp_config zfp_config_precision(uint precision);
+zfp_config zfp_config_accuracy(double tolerance);
+zfp_config zfp_config_reversible(void);
+zfp_config zfp_config_expert(uint minbits, uint maxbits, uint maxprec, int minexp);
 
 /* ---- the hot path (include/zfp.h:585-627; src/zfp.c:1051-1249) ----------------------------- */
 /* Both return the cumulative stream size in bytes, 0 on failure / unsupported.  field->data and

@@ -400,3 +400,75 @@ def test_zfpy_compatible_module_interoperates_with_reference(zb, ref):
     assert bytes(buf.cpu().numpy()[:4]) == b"zfp\x05"
     y = zfpy.decompress_tensor(c)
     assert float((x - y).abs().max()) <= 1e-4
+
+
+def test_one_zfp_stream_many_fields_then_decompress_an_earlier_one(zb, port):
+    """The block index a variable-rate compress leaves on its zfp_stream describes the LAST field
+    compressed.  A legal pattern - one zfp_stream compresses u, v, w of the same shape into three
+    buffers, then decompresses u - must not decode u with w's block lengths: the backend checks every
+    block's parsed length against the index and falls back to rebuilding it from the stream."""
+    import torch
+    from zfp_b200.api import Stream, _make_field, load_library
+    L = load_library()
+    shape = (24, 28, 36)
+    fields = [make_field(shape, np.float64, seed=s, kind=k) for s, k in ((3, "smooth"), (4, "noise"), (5, "sparse"))]
+    for mode in ({"accuracy": 1e-4}, {"precision": 21}, {"reversible": True}):
+        cap = zb.max_stream_words(shape, torch.float64, mode)
+        bufs = [torch.zeros(cap, dtype=torch.int64, device="cuda") for _ in fields]
+        s = Stream(bufs[0].data_ptr(), cap * 8, mode, 4, 3)
+        sizes = []
+        for a, buf in zip(fields, bufs):
+            bs = L.stream_open(buf.data_ptr(), cap * 8)
+            L.zfp_stream_set_bit_stream(s.z, bs)
+            x = torch.from_numpy(a).cuda()
+            f = _make_field(L, x.data_ptr(), 4, shape, None)
+            sizes.append(L.zfp_compress(s.z, f))
+            assert sizes[-1], zb.last_error()
+            L.zfp_field_free(f)
+            L.stream_close(bs)
+        for a, buf, nbytes in zip(fields, bufs, sizes):  # the first two decodes meet a stale index
+            bs = L.stream_open(buf.data_ptr(), cap * 8)
+            L.zfp_stream_set_bit_stream(s.z, bs)
+            out = torch.empty(shape, dtype=torch.float64, device="cuda")
+            f = _make_field(L, out.data_ptr(), 4, shape, None)
+            assert L.zfp_decompress(s.z, f) == nbytes, (mode, zb.last_error())
+            L.zfp_field_free(f)
+            L.stream_close(bs)
+            want = port.decompress(port.compress(a, **mode), shape, a.dtype, **mode)
+            assert out.cpu().numpy().tobytes() == want.tobytes(), mode
+        L.zfp_stream_set_bit_stream(s.z, s.bs)
+        s.close()
+
+
+def test_two_host_threads_two_zfp_streams_one_gpu(zb, port):
+    """Reference contract: thread-safe as long as threads do not share a zfp_stream
+    (docs/source/faq.rst:1096-1098).  Two threads compress and decompress different fields at the same
+    time on one device, host buffers and device buffers, all modes that use device scratch."""
+    import threading
+    import torch
+    errors = []
+
+    def worker(seed, kind):
+        try:
+            stream = torch.cuda.Stream()
+            for rep in range(6):
+                a = make_field((36, 40, 44), np.float64, seed=seed + rep, kind=kind)
+                for mode in ({"accuracy": 1e-3}, {"precision": 20}, {"rate": 7.5}):
+                    want = port.compress(a, **mode)
+                    got = zb.compress_numpy(a, **mode)[0]                       # host staging buffers
+                    assert got.tobytes() == want.tobytes(), ("host", seed, rep, mode)
+                    x = torch.from_numpy(a).cuda()
+                    c = zb.compress(x, cuda_stream=stream.cuda_stream, **mode)  # scan / slot scratch on a side stream
+                    assert c.to_numpy().tobytes() == want.tobytes(), ("device", seed, rep, mode)
+                    back = zb.decompress(c)
+                    stream.synchronize()
+                    assert back.cpu().numpy().tobytes() == port.decompress(want, a.shape, a.dtype, **mode).tobytes(), (seed, rep, mode)
+        except Exception as e:  # noqa: BLE001 - reported below
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(100, "smooth")), threading.Thread(target=worker, args=(200, "noise"))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

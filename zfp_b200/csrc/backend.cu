@@ -42,23 +42,72 @@ extern "C" const char* zfp_b200_last_error(void) { return g_error.c_str(); }
 extern "C" uint64 zfp_b200_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------------------------------
-// device scratch: grow-only buffers cached per (device, slot), released on request
+// device scratch: grow-only buffer SETS cached per device and leased to one call at a time.
+// The reference's contract is "thread-safe as long as threads do not share a zfp_stream"
+// (docs/source/faq.rst:1096-1098; its CUDA backend allocates per call).  Here every entry point takes
+// a lease for its duration: two host threads, or two CUDA streams, working on the same device get
+// different sets.  A call may return with its kernels still in flight (device_only_sync), so a set
+// goes back to the pool with an event recorded on the caller's stream and its next user makes its own
+// stream wait for that event first.  Growing a buffer frees the old one with cudaFree, which waits for
+// the device, so work still using it completes.
 // ------------------------------------------------------------------------------------------------
 namespace {
 
 enum { SCR_SLOTS = 0, SCR_LENGTHS, SCR_TILES, SCR_OFFSETS, SCR_CURSOR, SCR_STAGE_DATA, SCR_STAGE_WORDS, SCR_COUNT };
 
 struct ScratchBuf { void* p = nullptr; size_t bytes = 0; };
-struct DeviceScratch { ScratchBuf buf[SCR_COUNT]; };
+struct ScratchSet {
+  ScratchBuf buf[SCR_COUNT];
+  cudaEvent_t idle = nullptr;  // recorded when the last lease ended
+  bool recorded = false, busy = false;
+};
+constexpr int kMaxDevices = 64, kMaxSets = 16;
 std::mutex g_scratch_mutex;
-DeviceScratch g_scratch[64];
+ScratchSet* g_sets[kMaxDevices][kMaxSets];
+thread_local ScratchSet* t_lease = nullptr;
+
+class ScratchLease {
+ public:
+  explicit ScratchLease(cudaStream_t st) : st_(st)
+  {
+    if (t_lease) return;  // nested entry point: the outer call's set
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    for (int i = 0; i < kMaxSets && !set_; i++) {
+      if (!g_sets[dev][i]) g_sets[dev][i] = new (std::nothrow) ScratchSet();
+      if (g_sets[dev][i] && !g_sets[dev][i]->busy) set_ = g_sets[dev][i];
+    }
+    if (!set_) return;  // more than kMaxSets concurrent calls on one device: scratch() reports the failure
+    set_->busy = true;
+    if (set_->recorded) cudaStreamWaitEvent(st_, set_->idle, 0);
+    t_lease = set_;
+  }
+  ~ScratchLease()
+  {
+    if (!set_) return;
+    if (!set_->idle && cudaEventCreateWithFlags(&set_->idle, cudaEventDisableTiming) != cudaSuccess) set_->idle = nullptr;
+    set_->recorded = set_->idle && cudaEventRecord(set_->idle, st_) == cudaSuccess;
+    if (!set_->recorded) cudaStreamSynchronize(st_);
+    t_lease = nullptr;
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    set_->busy = false;
+  }
+  ScratchLease(const ScratchLease&) = delete;
+  ScratchLease& operator=(const ScratchLease&) = delete;
+
+ private:
+  cudaStream_t st_;
+  ScratchSet* set_ = nullptr;
+};
 
 void* scratch(int slot, size_t bytes)
 {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lock(g_scratch_mutex);
-  ScratchBuf& b = g_scratch[dev].buf[slot];
+  if (!t_lease) {
+    g_error = "no scratch set available (too many concurrent calls on this device)";
+    return nullptr;
+  }
+  ScratchBuf& b = t_lease->buf[slot];
   if (b.bytes < bytes) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr;
@@ -70,6 +119,20 @@ void* scratch(int slot, size_t bytes)
   return b.p;
 }
 
+// multiprocessors of the current device (grid sizing of the helper kernels)
+int sm_count()
+{
+  static std::atomic<int> cached[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 }  // namespace
 
 extern "C" void zfp_b200_release_scratch(void)
@@ -77,13 +140,17 @@ extern "C" void zfp_b200_release_scratch(void)
   std::lock_guard<std::mutex> lock(g_scratch_mutex);
   int cur = 0;
   cudaGetDevice(&cur);
-  for (int d = 0; d < 64; d++)
-    for (int s = 0; s < SCR_COUNT; s++)
-      if (g_scratch[d].buf[s].p) {
-        cudaSetDevice(d);
-        cudaFree(g_scratch[d].buf[s].p);
-        g_scratch[d].buf[s] = ScratchBuf();
-      }
+  for (int d = 0; d < kMaxDevices; d++)
+    for (int i = 0; i < kMaxSets; i++) {
+      ScratchSet* set = g_sets[d][i];
+      if (!set || set->busy) continue;
+      cudaSetDevice(d);
+      for (int k = 0; k < SCR_COUNT; k++)
+        if (set->buf[k].p) cudaFree(set->buf[k].p);
+      if (set->idle) cudaEventDestroy(set->idle);
+      delete set;
+      g_sets[d][i] = nullptr;
+    }
   cudaSetDevice(cur);
 }
 
@@ -95,7 +162,25 @@ struct zfp_b200_index {
   size_t blocks = 0;
   size_t capacity = 0;
   uint64_t total_bits = 0;  // sum of the lengths, recorded by the encode that filled the index
+  // what the lengths describe (filled by zfp_b200_encode): a decode with other parameters or another
+  // start phase ignores the index and rebuilds one; a decode that finds a block whose parsed length
+  // differs from the recorded one (same shape and parameters, other data) reports it and is redone
+  bool keyed = false;
+  zfp_b200_desc key_desc;
+  uint64_t key_start = 0;
 };
+
+static bool index_matches(const zfp_b200_index* ix, const zfp_b200_desc* d, const Geom& g, uint64_t start_bit)
+{
+  if (!ix || ix->blocks != g.nblocks) return false;
+  if (!ix->keyed) return true;  // imported lengths: the caller vouches for them (checked block by block during the decode)
+  const zfp_b200_desc& k = ix->key_desc;
+  bool same = k.type == d->type && k.dims == d->dims && k.minbits == d->minbits && k.maxbits == d->maxbits &&
+              k.maxprec == d->maxprec && k.minexp == d->minexp && (ix->key_start & 63) == (start_bit & 63);
+  for (uint32_t i = 0; i < d->dims && same; i++)
+    same = k.n[i] == d->n[i];
+  return same;
+}
 
 extern "C" zfp_b200_index* zfp_b200_index_create(void) { return new (std::nothrow) zfp_b200_index(); }
 
@@ -135,6 +220,8 @@ extern "C" int zfp_b200_index_import(zfp_b200_index* ix, const uint16_t* host, s
   if (!ix || !host) return ZFP_B200_EINVAL;
   if (!index_reserve(ix, blocks)) return ZFP_B200_ECUDA;
   CU(cudaMemcpy(ix->d_lengths, host, blocks * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  ix->keyed = false;
+  ix->total_bits = 0;
   return ZFP_B200_OK;
 }
 
@@ -190,6 +277,13 @@ static bool check_params(const zfp_b200_desc* d)
     g_error = "maxbits is smaller than the block header: parameters outside zfp_stream_maximum_size's contract";
     return false;
   }
+  // variable rate: block lengths travel as 16-bit words (the index format).  No block codes more than
+  // 16 658 bits of its own (4-D double, reversible), so only a minbits padding beyond 65 535 could
+  // overflow them: refused (expert parameters nobody uses) rather than wrapped.
+  if (d->minbits != d->maxbits && d->minbits > 65535) {
+    g_error = "variable-rate parameters with minbits > 65535 are not supported (16-bit block lengths)";
+    return false;
+  }
   return true;
 }
 
@@ -241,11 +335,12 @@ static int encode_any(int out_mode, int type, uint32_t dims, const void* data, c
 }
 
 static int decode_any(int offs_mode, int type, uint32_t dims, void* data, const Geom& g, const Params& prm, const void* in,
-                      uint64_t start_bit, const uint64_t* offsets, const uint16_t* lengths, cudaStream_t st, uint64_t b0, uint64_t b1)
+                      uint64_t start_bit, const uint64_t* offsets, const uint16_t* lengths, cudaStream_t st, uint64_t b0, uint64_t b1,
+                      uint32_t* check = nullptr)
 {
   static const int staged = getenv("ZFP_B200_NO_STAGED") ? 0 : 1;
   if (b0 >= b1) return ZFP_B200_OK;
-  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, lengths, st, staged, b0, b1 };
+  const DecodeArgs a = { data, g, prm, in, start_bit, offsets, lengths, st, staged, b0, b1, check };
   cudaError_t e;
   switch (type) {
     case T_INT32: e = launch_decode_t<T_INT32>((int)dims, offs_mode, a); break;
@@ -272,7 +367,8 @@ static int scan_lengths(const uint16_t* lengths, uint64_t n, uint64_t* tiles, ui
   return ZFP_B200_OK;
 }
 
-__global__ void set_cursor(uint64_t* cursor, uint64_t v) { cursor[0] = v; cursor[1] = v; }
+// cursor[0] = first bit, cursor[1] = running end, cursor[2] = decode-time index check (0 = lengths agree)
+__global__ void set_cursor(uint64_t* cursor, uint64_t v) { cursor[0] = v; cursor[1] = v; cursor[2] = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // raw entry points
@@ -290,6 +386,7 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
     return ZFP_B200_EINVAL;
   g_error.clear();
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ScratchLease lease(st);
   const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
   const int type = d->type;
   const uint32_t dims = d->dims;
@@ -351,7 +448,7 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
     if (rc) return rc;
     rc = scan_lengths(lengths + b0, cn, tiles, offsets, cursor, st);
     if (rc) return rc;
-    zero_new_words<<<148 * 4, 256, 0, st>>>(static_cast<uint64_t*>(d_words), cursor);
+    zero_new_words<<<sm_count() * 4, 256, 0, st>>>(static_cast<uint64_t*>(d_words), cursor);
     LAUNCHED();
     compact_blocks<<<(unsigned)((cn * kCompactLanes + 255) / 256), 256, 0, st>>>(slots, slot_words, lengths + b0, offsets, cn, d_words);
     LAUNCHED();
@@ -360,7 +457,12 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (end_bit) *end_bit = h_cursor[1];
-  if (index) index->total_bits = h_cursor[1] - start_bit;
+  if (index) {
+    index->total_bits = h_cursor[1] - start_bit;
+    index->keyed = true;
+    index->key_desc = *d;
+    index->key_start = start_bit;
+  }
   return ZFP_B200_OK;
 }
 
@@ -392,6 +494,7 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
     return ZFP_B200_EINVAL;
   g_error.clear();
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ScratchLease lease(st);
   const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
   int rc;
   if (whole) {
@@ -410,18 +513,19 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
     return ZFP_B200_OK;
   }
 
+  // An index that was made for other parameters, another shape or another bit phase is not used; one
+  // that passes is still checked block by block while decoding (the lengths it records against the
+  // lengths the parse finds): the same zfp_stream may have compressed another field of the same shape
+  // since, or the buffer may have been refilled.  A stale index costs one wasted decode, never wrong data.
   const uint16_t* lengths;
-  if (index && index->blocks == g.nblocks)
+  const bool use_index = index_matches(index, d, g, start_bit);
+  if (use_index)
     lengths = index->d_lengths;
-  else if (index && index->blocks) {
-    g_error = "zfp_b200_decode: block index does not match the field (wrong number of blocks)";
-    return ZFP_B200_ENOINDEX;
-  }
   else {
     // foreign stream: rebuild the index by parsing the stream sequentially on the device
     uint16_t* rebuilt = static_cast<uint16_t*>(scratch(SCR_LENGTHS, g.nblocks * sizeof(uint16_t)));
     if (!rebuilt) return ZFP_B200_ECUDA;
-    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, nullptr, st, 0, 0, g.nblocks };
+    const DecodeArgs a = { d_data, g, prm, d_words, start_bit, nullptr, nullptr, st, 0, 0, g.nblocks, nullptr };
     cudaError_t e;
     switch (d->type) {
       case T_INT32: e = launch_index_t<T_INT32>((int)d->dims, a, rebuilt); break;
@@ -441,11 +545,20 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
   LAUNCHED();
   rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st);
   if (rc) return rc;
-  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st, block0, block1);
+  rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st, block0, block1,
+                  reinterpret_cast<uint32_t*>(cursor + 2));
   if (rc) return rc;
-  uint64_t h_cursor[2];
+  uint64_t h_cursor[3];
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (h_cursor[2]) {
+    if (!use_index) {
+      g_error = "zfp_b200_decode: the stream does not parse to the lengths just rebuilt from it (corrupt stream?)";
+      return ZFP_B200_EINVAL;
+    }
+    // stale index: rebuild from the stream itself and decode again
+    return decode_range(d, d_data, d_words, start_bit, end_bit, nullptr, cuda_stream, block0, block1, whole);
+  }
   if (end_bit) *end_bit = h_cursor[1];
   return ZFP_B200_OK;
 }
@@ -457,7 +570,8 @@ extern "C" int zfp_b200_bitcopy(void* d_dst_words, uint64 dst_bit, const void* d
   if (!d_dst_words || !d_src_words) return ZFP_B200_EINVAL;
   const uint64_t words = ((dst_bit + nbits + 63) >> 6) - (dst_bit >> 6);
   unsigned ctas = (unsigned)((words + 255) / 256);
-  if (ctas > 148 * 16) ctas = 148 * 16;
+  const unsigned cap = (unsigned)sm_count() * 16;
+  if (ctas > cap) ctas = cap;
   bitcopy_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(static_cast<uint64_t*>(d_dst_words), dst_bit,
                                                                            static_cast<const uint64_t*>(d_src_words), src_bit, nbits);
   LAUNCHED();
@@ -635,6 +749,7 @@ static size_t compress_impl(zfp_stream* zfp, const zfp_field* field)
   if (!s || !field->data || !fill_desc(zfp, field, &d)) return 0;
   zfp_exec_params_cuda* xp = get_cuda_params(zfp);
   cudaStream_t st = xp ? static_cast<cudaStream_t>(xp->cuda_stream) : nullptr;
+  ScratchLease lease(st);
   const size_t esize = scalar_bytes(d.type);
   const uint64_t start_bit = (uint64_t)(s->ptr - s->begin) * 64 + s->bits;
   const uint64_t first_word = start_bit >> 6;
@@ -712,6 +827,7 @@ static size_t decompress_impl(zfp_stream* zfp, zfp_field* field)
   if (!s || !field->data || !fill_desc(zfp, field, &d)) return 0;
   zfp_exec_params_cuda* xp = get_cuda_params(zfp);
   cudaStream_t st = xp ? static_cast<cudaStream_t>(xp->cuda_stream) : nullptr;
+  ScratchLease lease(st);
   const size_t esize = scalar_bytes(d.type);
   const uint64_t start_bit = (uint64_t)(s->ptr - s->begin) * 64 - s->bits;
   const uint64_t first_word = start_bit >> 6;

@@ -33,6 +33,11 @@
 
 namespace zb {
 
+// developer switch for A/B timing: 0 removes the narrow (32-bit) plane steps of the 64-value coders
+#ifndef ZB_NARROW
+#define ZB_NARROW 0
+#endif
+
 template <int TYPE> struct Traits;
 template <> struct Traits<T_INT32> {
   using Scalar = int32_t; using Int = int32_t; using UInt = uint32_t;
@@ -300,6 +305,9 @@ struct ColReader {
   // (32-bit words) and number `left` from there; restage() slides the window
   const uint32_t* gsrc;
   uint32_t left, cap;
+  // shared-space address of the 32-entry table of test-bit positions used by the run decoder
+  // (decode_planes_events): entry n has bits n, 2n+1, 3n+2, ... below 32 set
+  uint32_t pm;
 
   __device__ __forceinline__ void init(const uint32_t* column)
   {
@@ -307,6 +315,22 @@ struct ColReader {
     bp = 0;
     gsrc = nullptr;
     left = cap = 0;
+    pm = 0;
+  }
+  __device__ __forceinline__ void set_run_table(const uint32_t* table) { pm = (uint32_t)__cvta_generic_to_shared(table); }
+  // fill the table (one thread per entry; the caller synchronises the CTA afterwards)
+  __device__ static __forceinline__ void fill_run_table(uint32_t* table, uint32_t n)
+  {
+    uint32_t m = 0;
+    for (uint32_t pos = n; pos < 32; pos += n + 1)
+      m |= 1u << pos;
+    table[n] = m;
+  }
+  __device__ __forceinline__ uint32_t run_mask(uint32_t n) const  // n < 32
+  {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pm + (n << 2)));
+    return v;
   }
   __device__ __forceinline__ void stage()
   {
@@ -321,6 +345,7 @@ struct ColReader {
     cap = capacity_words;
     gsrc = src;
     left = words;
+    pm = 0;
     stage();
     bp = phase;
   }
@@ -445,16 +470,42 @@ __device__ __forceinline__ void xform_inv(Int (&p)[1 << (2 * DIMS)])
 // ------------------------------------------------------------------------------------------------
 // 32x32 bit-matrix transpose in registers: on return bit i of a[j] is the former bit j of a[i]
 // ------------------------------------------------------------------------------------------------
-template <int J>
+// one LOP3 with an explicit truth table (the compiler splits (x & m) | (y & ~m) into two operations
+// with two immediates when left to itself).  Table bit i = f(a, b, c) for (a, b, c) = bits 2, 1, 0 of i.
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return r;
+}
+// (x & m) | (y & ~m), optionally with y or the result inverted
+template <int NEG>
+__device__ __forceinline__ uint32_t bitselect(uint32_t x, uint32_t y, uint32_t m)
+{
+  return NEG == 0 ? lop3<0xE4>(x, y, m) : NEG == 2 ? lop3<0xB1>(x, y, m) : lop3<0x1B>(x, y, m);
+}
+// One butterfly stage: rows k and k+J exchange the column groups selected by m.  Written as two
+// bit-selects (one LOP3 each) on the shifted partner instead of the classic xor-swap
+// (shift, xor-and, xor, shift, xor): 3 ALU-pipe instructions + 1 left shift that ptxas may place on
+// the FMA pipe (IMAD.SHL) per pair instead of 5.
+// NEG folds the negabinary mask 0xaaaa... (encode.c:75-88 int2uint, decode.c:63-76 uint2int) into the
+// J == 1 stage: XOR with the mask is "invert every odd bit plane", i.e. every odd row on the plane
+// side of the transpose, and an inverted input or output costs nothing in a LOP3.
+//   NEG 0: plain.   NEG 1: odd OUTPUT rows inverted (coefficients -> planes, J == 1 is the last stage).
+//   NEG 2: odd INPUT rows inverted (planes -> coefficients, J == 1 is the first stage).
+// (The butterfly stages swap independent index bits, so they commute.)
+template <int J, int NEG = 0>
 __device__ __forceinline__ void transpose32_stage(uint32_t (&a)[32])
 {
   constexpr uint32_t m = J == 16 ? 0x0000ffffu : J == 8 ? 0x00ff00ffu : J == 4 ? 0x0f0f0f0fu : J == 2 ? 0x33333333u : 0x55555555u;
+  static_assert(NEG == 0 || J == 1, "the negabinary fold lives in the J == 1 stage");
 #pragma unroll
   for (int k = 0; k < 32; k++)
     if (!(k & J)) {
       // swap (row k, columns c+J) with (row k+J, columns c) for the columns c selected by m
       if (J == 16) {
-        // halfword granularity: two byte permutes instead of shift/xor/and
+        // halfword granularity: two byte permutes instead of shifts and selects
         const uint32_t lo = __byte_perm(a[k], a[k + J], 0x5410), hi = __byte_perm(a[k], a[k + J], 0x7632);
         a[k] = lo;
         a[k + J] = hi;
@@ -465,30 +516,35 @@ __device__ __forceinline__ void transpose32_stage(uint32_t (&a)[32])
         a[k + J] = hi;
       }
       else {
-        uint32_t t = ((a[k] >> J) ^ a[k + J]) & m;
-        a[k + J] ^= t;
-        a[k] ^= t << J;
+        // NEG 2: row k+J comes in inverted (both selects take ~r1); NEG 1: row k+J goes out inverted
+        const uint32_t r0 = a[k], r1 = a[k + J];
+        a[k] = bitselect<NEG == 2 ? 2 : 0>(r0, r1 << J, m);
+        a[k + J] = bitselect<NEG>(r0 >> J, r1, m);
       }
     }
 }
 
+template <int NEG = 0>
 __device__ __forceinline__ void transpose32(uint32_t (&a)[32])
 {
+  if (NEG == 2) transpose32_stage<1, NEG>(a);
   transpose32_stage<16>(a);
   transpose32_stage<8>(a);
   transpose32_stage<4>(a);
   transpose32_stage<2>(a);
-  transpose32_stage<1>(a);
+  if (NEG != 2) transpose32_stage<1, NEG>(a);
 }
 
 // Small blocks (M = 16 or 4 coefficients): the 32-bit words of the M coefficients form 32/M square
 // M x M bit matrices side by side; transposing each in place (log2 M butterfly stages on M words,
 // the masks are periodic so all matrices go at once) leaves word i = [plane i | plane M+i | ...],
-// M bits each.  A quarter / a sixteenth of the work of padding to a 32x32 matrix.
-template <int J, int M>
+// M bits each (plane parity = row parity, so the negabinary fold works as above).  A quarter / a
+// sixteenth of the work of padding to a 32x32 matrix.
+template <int J, int M, int NEG = 0>
 __device__ __forceinline__ void transpose_small_stage(uint32_t (&a)[M])
 {
   constexpr uint32_t m = J == 8 ? 0x00ff00ffu : J == 4 ? 0x0f0f0f0fu : J == 2 ? 0x33333333u : 0x55555555u;
+  static_assert(NEG == 0 || J == 1, "the negabinary fold lives in the J == 1 stage");
 #pragma unroll
   for (int k = 0; k < M; k++)
     if (!(k & J)) {
@@ -498,19 +554,21 @@ __device__ __forceinline__ void transpose_small_stage(uint32_t (&a)[M])
         a[k + J] = hi;
       }
       else {
-        uint32_t t = ((a[k] >> J) ^ a[k + J]) & m;
-        a[k + J] ^= t;
-        a[k] ^= t << J;
+        // NEG 2: row k+J comes in inverted (both selects take ~r1); NEG 1: row k+J goes out inverted
+        const uint32_t r0 = a[k], r1 = a[k + J];
+        a[k] = bitselect<NEG == 2 ? 2 : 0>(r0, r1 << J, m);
+        a[k + J] = bitselect<NEG>(r0 >> J, r1, m);
       }
     }
 }
-template <int M>
+template <int M, int NEG = 0>
 __device__ __forceinline__ void transpose_small(uint32_t (&a)[M])
 {
+  if (NEG == 2) transpose_small_stage<1, M, NEG>(a);
   if constexpr (M >= 16) transpose_small_stage<8, M>(a);
   if constexpr (M >= 8) transpose_small_stage<4, M>(a);
   transpose_small_stage<2, M>(a);
-  transpose_small_stage<1, M>(a);
+  if (NEG != 2) transpose_small_stage<1, M, NEG>(a);
 }
 
 // Plane storage in shared memory: plane k of the calling lane is sp[k * 32] where sp already
@@ -518,8 +576,19 @@ __device__ __forceinline__ void transpose_small(uint32_t (&a)[M])
 template <int N> struct PlaneWord { using type = uint32_t; };
 template <> struct PlaneWord<64> { using type = uint64_t; };
 
+// In all plane conversions NEG says where the negabinary mask is (see transpose32_stage): with
+// NEG = 1 the input words are "pre-negabinary" coefficients q + 0xaaaa... and the planes come out as
+// those of (q + mask) ^ mask; with NEG = 2 the planes go in as stored and the words come out as
+// u ^ 0xaaaa..., to which the caller applies the subtraction (planes that were never decoded read
+// as zero, so their bits come out as the mask's: u ^ mask for u = 0).  NEG = 0 (reversible mode,
+// whose precision scan needs the true negabinary words) leaves both sides alone.
+template <int NEG> struct NegaWord {
+  static constexpr uint32_t w32 = NEG ? 0xaaaaaaaau : 0u;        // what a word of the NEG-side representation holds for u = 0
+  static constexpr uint64_t w64 = NEG ? 0xaaaaaaaaaaaaaaaaull : 0ull;
+};
+
 // coefficients (sequency order) -> bit planes
-template <class UInt, int N>
+template <int NEG, class UInt, int N>
 __device__ __forceinline__ void to_planes(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
 {
   constexpr int P = 8 * (int)sizeof(UInt);
@@ -531,8 +600,8 @@ __device__ __forceinline__ void to_planes(const UInt (&u)[N], typename PlaneWord
     for (int g = 0; g < G; g++) {
 #pragma unroll
       for (int i = 0; i < 32; i++)
-        a[g][i] = (32 * g + i < N) ? (uint32_t)(u[(32 * g + i) % N] >> (32 * h)) : 0u;
-      transpose32(a[g]);
+        a[g][i] = (32 * g + i < N) ? (uint32_t)(u[(32 * g + i) % N] >> (32 * h)) : NegaWord<NEG>::w32;
+      transpose32<NEG>(a[g]);
     }
 #pragma unroll
     for (int k = 0; k < 32; k++) {
@@ -545,7 +614,7 @@ __device__ __forceinline__ void to_planes(const UInt (&u)[N], typename PlaneWord
 }
 
 // bit planes -> coefficients; planes below kstop were never written and read as zero
-template <class UInt, int N>
+template <int NEG, class UInt, int N>
 __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWord<N>::type* sp, int kstop)
 {
   constexpr int P = 8 * (int)sizeof(UInt);
@@ -565,7 +634,7 @@ __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWo
     }
 #pragma unroll
     for (int g = 0; g < G; g++) {
-      transpose32(a[g]);
+      transpose32<NEG>(a[g]);
 #pragma unroll
       for (int i = 0; i < 32; i++)
         if (32 * g + i < N)
@@ -574,46 +643,69 @@ __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWo
   }
 }
 
+// 32-bit half H of word u replaced by v
+template <int H> __device__ __forceinline__ void set_half(uint32_t& u, uint32_t v) { u = v; }
+template <int H> __device__ __forceinline__ void set_half(uint64_t& u, uint32_t v)
+{
+  u = H ? ((u & 0xffffffffull) | ((uint64_t)v << 32)) : ((u & 0xffffffff00000000ull) | v);
+}
+
 // Two-phase variants for the staged fast path: only 32 planes (bits 32H .. 32H+31 of every
 // coefficient) are resident in shared memory at a time, as sp[(k - 32H) * 32].  Halves the plane
 // storage (more resident warps) and skips the low half entirely when no block of the warp needs it.
-template <int H, class UInt, int N>
-__device__ __forceinline__ void to_planes_half(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
+// Blocks of 64 values: returns `kup`, the number of planes at the bottom of this set (0..32) in which
+// some block of the warp has a bit beyond coefficient 31 (one warp-wide OR of the words of
+// coefficients 32..63; on smooth data the high-sequency coefficients are small and only the lowest
+// coded planes reach them).  Planes kup.. of the set are 32-bit work for the coder (narrow plane
+// steps), and with kup == 0 the words of coefficients 32..63 are not transposed at all.
+template <int H, int NEG, class UInt, int N>
+__device__ __forceinline__ int to_planes_half(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
 {
   if constexpr (N == 16 || N == 4) {
     uint32_t a[N];
 #pragma unroll
     for (int i = 0; i < N; i++)
       a[i] = (uint32_t)(u[i] >> (32 * H));
-    transpose_small<N>(a);
+    transpose_small<N, NEG>(a);
 #pragma unroll
     for (int q = 0; q < 32 / N; q++)
 #pragma unroll
       for (int i = 0; i < N; i++)
         sp[(N * q + i) * 32] = (a[i] >> (N * q)) & ((1u << N) - 1);
-    return;
+    return 0;
   }
-  constexpr int G = (N + 31) / 32;
-  uint32_t a[G][32];
+  else {
+    static_assert(N == 64, "blocks of 4, 16 or 64 values");
+    uint32_t a0[32], a1[32];
+    uint32_t any_upper = 0;
 #pragma unroll
-  for (int g = 0; g < G; g++) {
+    for (int i = 0; i < 32; i++) {
+      a0[i] = (uint32_t)(u[i] >> (32 * H));
+      a1[i] = (uint32_t)(u[32 + i] >> (32 * H));
+      any_upper |= a1[i] ^ NegaWord<NEG>::w32;
+    }
+    const int kup = 32 - __clz((int)__reduce_or_sync(0xffffffffu, any_upper));
+    transpose32<NEG>(a0);
+    if (kup == 0) {
 #pragma unroll
-    for (int i = 0; i < 32; i++)
-      a[g][i] = (32 * g + i < N) ? (uint32_t)(u[(32 * g + i) % N] >> (32 * H)) : 0u;
-    transpose32(a[g]);
-  }
+      for (int k = 0; k < 32; k++)
+        sp[k * 32] = (uint64_t)a0[k];
+    }
+    else {
+      transpose32<NEG>(a1);
 #pragma unroll
-  for (int k = 0; k < 32; k++) {
-    if (G == 2)
-      sp[k * 32] = (typename PlaneWord<N>::type)((uint64_t)a[0][k] | ((uint64_t)a[G - 1][k] << 32));
-    else
-      sp[k * 32] = (typename PlaneWord<N>::type)a[0][k];
+      for (int k = 0; k < 32; k++)
+        sp[k * 32] = (uint64_t)a0[k] | ((uint64_t)a1[k] << 32);
+    }
+    return kup;
   }
 }
 
-// OR planes 32H .. 32H+31 (those with absolute index >= kstop; the rest read as zero) into u
-template <int H, class UInt, int N>
-__device__ __forceinline__ void from_planes_half(UInt (&u)[N], const typename PlaneWord<N>::type* sp, int kstop)
+// Planes 32H .. 32H+31 (those with absolute index >= kstop; the rest read as zero) replace half H of
+// every word of u.  `upper` = false: no block of the warp has a significant coefficient beyond the
+// 32nd, so the words of coefficients 32..63 keep the value they were initialised with (u = 0).
+template <int H, int NEG, class UInt, int N>
+__device__ __forceinline__ void from_planes_half(UInt (&u)[N], const typename PlaneWord<N>::type* sp, int kstop, bool upper = true)
 {
   if constexpr (N == 16 || N == 4) {
     uint32_t a[N];
@@ -627,28 +719,30 @@ __device__ __forceinline__ void from_planes_half(UInt (&u)[N], const typename Pl
         const uint32_t x = (32 * H + N * q + i >= kstop) ? (uint32_t)sp[(N * q + i) * 32] : 0u;
         a[i] |= x << (N * q);
       }
-    transpose_small<N>(a);
+    transpose_small<N, NEG>(a);
 #pragma unroll
     for (int i = 0; i < N; i++)
-      u[i] |= (UInt)((UInt)a[i] << (32 * H));
-    return;
+      set_half<H>(u[i], a[i]);
   }
-  constexpr int G = (N + 31) / 32;
-  uint32_t a[G][32];
+  else {
+    static_assert(N == 64, "blocks of 4, 16 or 64 values");
+    uint32_t a0[32], a1[32];
 #pragma unroll
-  for (int k = 0; k < 32; k++) {
-    typename PlaneWord<N>::type x = (32 * H + k >= kstop) ? sp[k * 32] : 0;
-    a[0][k] = (uint32_t)x;
-    if (G == 2)
-      a[G - 1][k] = (uint32_t)((uint64_t)x >> 32);
-  }
-#pragma unroll
-  for (int g = 0; g < G; g++) {
-    transpose32(a[g]);
+    for (int k = 0; k < 32; k++) {
+      const uint64_t x = (32 * H + k >= kstop) ? sp[k * 32] : 0;
+      a0[k] = (uint32_t)x;
+      a1[k] = (uint32_t)(x >> 32);
+    }
+    transpose32<NEG>(a0);
 #pragma unroll
     for (int i = 0; i < 32; i++)
-      if (32 * g + i < N)
-        u[(32 * g + i) % N] |= (UInt)((UInt)a[g][i] << (32 * H));
+      set_half<H>(u[i], a0[i]);
+    if (upper) {
+      transpose32<NEG>(a1);
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        set_half<H>(u[32 + i], a1[i]);
+    }
   }
 }
 
@@ -656,53 +750,102 @@ __device__ __forceinline__ void from_planes_half(UInt (&u)[N], const typename Pl
 // 16W .. 16W+15 are resident as sp[(k - 16W) * 32].  Rows r = 16 rb + l of the bit matrix hold the
 // 16-bit slices of coefficients 32 rb + l (low half) and 32 rb + 16 + l (high half); transposing
 // every 16x16 block in place (the last four butterfly stages - the halfword stage is what the
-// packing already did) leaves row 16 rb + i = plane i of coefficients 32 rb .. 32 rb + 31.  Same
-// cost per plane as the 32-plane halves, but blocks that stop a few planes into the low half - the
-// usual case at rates around 8 - pay for 16 more planes instead of 32.
+// packing already did) leaves row 16 rb + i = plane i of coefficients 32 rb .. 32 rb + 31 (plane
+// parity = row parity).  Same cost per plane as the 32-plane halves, but blocks that stop a few planes
+// into the low half - the usual case at rates around 8 - pay for 16 more planes instead of 32.
 // The window is 16-bit slice w (0 or 1, a run-time value: it only changes a byte-permute selector)
 // of 32-bit half H (compile time: it selects registers), so the coder loop that follows is
-// instantiated once per half, not once per window.
-template <int H>
-__device__ __forceinline__ void to_planes_window(const uint64_t (&u)[64], uint64_t* sp, uint32_t w)
+// instantiated once per half, not once per window.  Returns kup (0..16) as to_planes_half does; rows
+// 16..31 (coefficients 32..63) are skipped when it is 0.
+template <int J, int NEG>
+__device__ __forceinline__ void transpose16_stage(uint32_t (&a)[16])
 {
-  const uint32_t sel = w ? 0x7632u : 0x5410u;
-  uint32_t a[32];
+  constexpr uint32_t m = J == 8 ? 0x00ff00ffu : J == 4 ? 0x0f0f0f0fu : J == 2 ? 0x33333333u : 0x55555555u;
 #pragma unroll
-  for (int r = 0; r < 32; r++) {
-    const int rb = r >> 4, l = r & 15;
-    a[r] = __byte_perm((uint32_t)(u[32 * rb + l] >> (32 * H)), (uint32_t)(u[32 * rb + 16 + l] >> (32 * H)), sel);
-  }
-  transpose32_stage<8>(a);
-  transpose32_stage<4>(a);
-  transpose32_stage<2>(a);
-  transpose32_stage<1>(a);
-#pragma unroll
-  for (int i = 0; i < 16; i++)
-    sp[i * 32] = (uint64_t)a[i] | ((uint64_t)a[16 + i] << 32);
+  for (int k = 0; k < 16; k++)
+    if (!(k & J)) {
+      if (J == 8) {
+        const uint32_t lo = __byte_perm(a[k], a[k + J], 0x6240), hi = __byte_perm(a[k], a[k + J], 0x7351);
+        a[k] = lo;
+        a[k + J] = hi;
+      }
+      else {
+        // NEG 2: row k+J comes in inverted (both selects take ~r1); NEG 1: row k+J goes out inverted
+        const uint32_t r0 = a[k], r1 = a[k + J];
+        a[k] = bitselect<NEG == 2 ? 2 : 0>(r0, r1 << J, m);
+        a[k + J] = bitselect<NEG>(r0 >> J, r1, m);
+      }
+    }
+}
+// two 16x16 bit matrices side by side (low / high halfword of 16 words), each transposed in place
+template <int NEG>
+__device__ __forceinline__ void transpose16x2(uint32_t (&a)[16])
+{
+  if (NEG == 2) transpose16_stage<1, NEG>(a);
+  transpose16_stage<8, 0>(a);
+  transpose16_stage<4, 0>(a);
+  transpose16_stage<2, 0>(a);
+  if (NEG != 2) transpose16_stage<1, NEG>(a);
 }
 
-// OR planes 16W .. 16W+15 (those with absolute index >= kstop; the rest read as zero) into u.
-// Compile-time window: the decoder measured faster with one coder-loop instance per window
-// (1024^3 fp64 rate 8: 6.1 ms against 6.4 ms), the encoder with one per half.
-template <int W>
-__device__ __forceinline__ void from_planes_window(uint64_t (&u)[64], const uint64_t* sp, int kstop)
+template <int H, int NEG>
+__device__ __forceinline__ int to_planes_window(const uint64_t (&u)[64], uint64_t* sp, uint32_t w)
 {
-  uint32_t a[32];
+  const uint32_t sel = w ? 0x7632u : 0x5410u;
+  uint32_t a0[16], a1[16];
+  uint32_t any_upper = 0;
+#pragma unroll
+  for (int l = 0; l < 16; l++) {
+    a0[l] = __byte_perm((uint32_t)(u[l] >> (32 * H)), (uint32_t)(u[16 + l] >> (32 * H)), sel);
+    a1[l] = __byte_perm((uint32_t)(u[32 + l] >> (32 * H)), (uint32_t)(u[48 + l] >> (32 * H)), sel);
+    any_upper |= a1[l] ^ NegaWord<NEG>::w32;
+  }
+  const uint32_t any_all = __reduce_or_sync(0xffffffffu, any_upper);  // two 16-bit slices per word
+  const int kup = 32 - __clz((int)((any_all | (any_all >> 16)) & 0xffffu));
+  transpose16x2<NEG>(a0);
+  if (kup == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      sp[i * 32] = (uint64_t)a0[i];
+  }
+  else {
+    transpose16x2<NEG>(a1);
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      sp[i * 32] = (uint64_t)a0[i] | ((uint64_t)a1[i] << 32);
+  }
+  return kup;
+}
+
+// Planes 16W .. 16W+15 (those with absolute index >= kstop; the rest read as zero) replace bits
+// 16W .. 16W+15 of every word of u.  Compile-time window: the decoder measured faster with one
+// coder-loop instance per window (1024^3 fp64 rate 8: 6.1 ms against 6.4 ms), the encoder with one
+// per half.  `upper` as in from_planes_half.
+template <int W, int NEG>
+__device__ __forceinline__ void from_planes_window(uint64_t (&u)[64], const uint64_t* sp, int kstop, bool upper = true)
+{
+  uint32_t a0[16], a1[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     const uint64_t x = (16 * W + i >= kstop) ? sp[i * 32] : 0;
-    a[i] = (uint32_t)x;
-    a[16 + i] = (uint32_t)(x >> 32);
+    a0[i] = (uint32_t)x;
+    a1[i] = (uint32_t)(x >> 32);
   }
-  transpose32_stage<8>(a);
-  transpose32_stage<4>(a);
-  transpose32_stage<2>(a);
-  transpose32_stage<1>(a);
+  // 16-bit slice W of the low word of u replaced by the low (coefficient l) / high (16 + l) halfword of a
+  constexpr uint32_t sel_lo = W ? 0x1054u : 0x7610u, sel_hi = W ? 0x3254u : 0x7632u;  // __byte_perm(a, u_lo, sel): bytes 0-3 = a, 4-7 = u_lo
+  transpose16x2<NEG>(a0);
 #pragma unroll
-  for (int r = 0; r < 32; r++) {
-    const int rb = r >> 4, l = r & 15;
-    u[32 * rb + l] |= (uint64_t)(a[r] & 0xffffu) << (16 * W);
-    u[32 * rb + 16 + l] |= (uint64_t)(a[r] >> 16) << (16 * W);
+  for (int l = 0; l < 16; l++) {
+    u[l] = (u[l] & 0xffffffff00000000ull) | __byte_perm(a0[l], (uint32_t)u[l], sel_lo);
+    u[16 + l] = (u[16 + l] & 0xffffffff00000000ull) | __byte_perm(a0[l], (uint32_t)u[16 + l], sel_hi);
+  }
+  if (upper) {
+    transpose16x2<NEG>(a1);
+#pragma unroll
+    for (int l = 0; l < 16; l++) {
+      u[32 + l] = (u[32 + l] & 0xffffffff00000000ull) | __byte_perm(a1[l], (uint32_t)u[32 + l], sel_lo);
+      u[48 + l] = (u[48 + l] & 0xffffffff00000000ull) | __byte_perm(a1[l], (uint32_t)u[48 + l], sel_hi);
+    }
   }
 }
 
@@ -846,17 +989,84 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
   }
 }
 
-// planes k-1 .. klo of the resident half (first plane kbase), two per vote (k and klo are even)
+// Narrow plane steps (blocks of 64 values), two planes per call.  Precondition, established by the
+// caller for every block of the warp: neither plane word has a bit beyond coefficient 31 and
+// pos <= 32.  Then a plane is 32-bit arithmetic: its n verbatim bits and T form one string of at most
+// 64 bits, and the formulas need no case split on an empty region: with y == 0, msb = -1 and c = 0
+// give tlen = msb + c + 2 = 1 (the lone '0' test), T = 0 and top = n.  A finished lane codes an empty
+// plane word with n = 0 and a zero-length string.  Returns false - with nothing appended and no state
+// changed - when some lane has more than four new coefficients in a plane or a T longer than 32 bits;
+// the caller then runs the general steps on this pair of planes.
+struct NarrowPlane {
+  uint32_t lo, hi, len, top;  // the plane string (len <= 64) and the coefficients settled after it
+  bool fits;
+};
+__device__ __forceinline__ NarrowPlane narrow_plane_string(bool d, uint32_t pos, uint32_t x)
+{
+  NarrowPlane r;
+  const uint32_t n = d ? 0u : pos;
+  const uint32_t xg = d ? 0u : x;
+  const uint32_t y = shr32c(xg, n);                 // n == 32: empty region
+  const uint32_t verb = xg ^ shl32c(y, n);
+  const uint32_t c = (uint32_t)__popc(y);
+  const int msb = 31 - __clz((int)y);                // -1 when y == 0
+  const uint32_t r1 = y & (y - 1), r2 = r1 & (r1 - 1), r3 = r2 & (r2 - 1), r4 = r3 & (r3 - 1);
+  const int keep = msb + (int)c;                     // data bits + flags of T, minus the leading test and the closing flag
+  r.fits = r4 == 0 && keep <= 30;
+  const uint32_t yp = y + r1 + 2 * r2 + 4 * r3;      // every one-bit moved up by its rank
+  const uint32_t e = (yp * 3u) & mask32((uint32_t)keep);  // (keep = -1: y == 0 and e == 0 whatever the mask)
+  const uint32_t tval = 2 * e + (y != 0 ? 1u : 0u);
+  const uint32_t tlen = d ? 0u : (uint32_t)(keep + 2);
+  r.lo = verb | shl32c(tval, n);
+  r.hi = __funnelshift_lc(tval, 0u, n);              // n <= 32, tlen <= 32
+  r.len = n + tlen;
+  r.top = n + (uint32_t)(msb + 1);
+  return r;
+}
+
+template <int N>
+__device__ __forceinline__ bool encode_pair_narrow(ColWriter& bw, uint32_t limit, int kmin, int k, uint32_t& pos, bool& done,
+                                                   const uint32_t x1, const uint32_t x2)
+{
+  bw.drain_if_low();
+  const uint32_t at = bw.tell();
+  const bool d1 = done || k - 1 < kmin || at >= limit;
+  const NarrowPlane p1 = narrow_plane_string(d1, pos, x1);
+  const bool d2 = d1 || k - 2 < kmin || at + p1.len >= limit;
+  const NarrowPlane p2 = narrow_plane_string(d2, p1.top, x2);
+  if (__any_sync(0xffffffffu, !(p1.fits && p2.fits)))
+    return false;
+  bw.append64(p1.lo, p1.hi, p1.len);
+  bw.append64(p2.lo, p2.hi, p2.len);
+  done = d2;
+  pos = p2.top;  // (a finished lane's pos is never looked at again)
+  return true;
+}
+
+// planes k-1 .. klo of the resident set (first plane kbase), two per vote (k and klo are even).
+// knarrow (warp uniform, blocks of 64 values): planes >= knarrow of the set have no bit beyond
+// coefficient 31 in any block of the warp (to_planes_half / to_planes_window); together with
+// pos <= 32 everywhere that selects the narrow plane steps.
 template <int N>
 __device__ __forceinline__ void encode_planes_lockstep(ColWriter& bw, uint32_t limit, int kmin, int klo, int kbase,
-                                                       LockState& st, const typename PlaneWord<N>::type* sp)
+                                                       LockState& st, const typename PlaneWord<N>::type* sp, int knarrow = 1 << 30)
 {
   constexpr uint32_t FULL = 0xffffffffu;
   uint32_t pos = st.pos;
   bool done = st.done;
   int k = st.k;
+  if constexpr (N > 32 && ZB_NARROW) {
+    if (__any_sync(FULL, pos > 32))
+      knarrow = 1 << 30;
+  }
   while (k > klo && __any_sync(FULL, !done)) {
     const typename PlaneWord<N>::type x1 = sp[(k - 1 - kbase) * 32], x2 = sp[(k - 2 - kbase) * 32];
+    if constexpr (N > 32 && ZB_NARROW) {
+      if (k - 2 >= knarrow && encode_pair_narrow<N>(bw, limit, kmin, k, pos, done, (uint32_t)x1, (uint32_t)x2)) {
+        k -= 2;
+        continue;
+      }
+    }
     encode_plane_lockstep<N>(bw, limit, kmin, k - 1, pos, done, x1);
     encode_plane_lockstep<N>(bw, limit, kmin, k - 2, pos, done, x2);
     k -= 2;
@@ -1056,6 +1266,72 @@ __device__ __forceinline__ void decode_plane_lockstep(ColReader& br, int kmin, i
   }
 }
 
+// Narrow plane steps (blocks of 64 values), two planes per call: the mirror of encode_pair_narrow.
+// Precondition: n <= 32 in every block of the warp.  Verbatim bits and T of a plane come from one
+// 64-bit look at the stream; when the plane ends with at most 32 significant coefficients its plane
+// word is 32 bits and is complete at once (no deferred verbatim fetch).  The second plane is parsed
+// from the first one's tentative results and ONE vote covers both: false - with no state changed and
+// nothing stored - when some lane needs the general step for either plane (more than four new
+// coefficients, a T the 32-bit window cannot hold, the budget running out inside T, or a coefficient
+// beyond the 32nd becoming significant).
+struct NarrowParse {
+  uint32_t x, bits, bp, n;  // plane word; budget, read position and significant count after the plane
+  bool dn, ok;
+};
+__device__ __forceinline__ NarrowParse narrow_plane_parse(const ColReader& br, bool dn, uint32_t bits, uint32_t bp, uint32_t n)
+{
+  NarrowParse r;
+  const uint32_t m = dn ? 0u : (n < bits ? n : bits);  // verbatim bits (<= 32 when the precondition holds)
+  uint32_t lo, hi;
+  br.peek64(bp, lo, hi);
+  const uint32_t verb = lo & mask32(m);
+  const uint32_t w = __funnelshift_rc(lo, hi, m);      // T starts here (m == 32: the high word)
+  const uint32_t left = bits - m;                      // budget at T
+  const bool test = !dn && left != 0;                  // (n <= 32 < N: there is always a group test)
+  // parse T as in decode_plane_lockstep: W' = virtual data bit, then the stream
+  const uint32_t wv = (w << 1) | 1u;
+  const uint32_t s = wv & ~(wv << 1);                    // run starts
+  const uint32_t ae = wv + (s & 0x55555555u), ao = wv + (s & 0xaaaaaaaau);
+  const uint32_t term = (ae & ~wv & 0xaaaaaaaau) | (ao & ~wv & 0x55555555u);  // just past each odd-length run
+  const uint32_t tl = term & (0u - term);                // lowest end mark; tl - 1 masks the bits of T
+  const uint32_t tpos = 31u - (uint32_t)__clz((int)tl);  // bits of T (0xffffffff when no end in the window)
+  const uint32_t d = ((wv & ~ae & 0x55555554u) | (wv & ~ao & 0xaaaaaaaau)) & (tl - 1) & (test ? ~0u : 0u);
+  const uint32_t c = (uint32_t)__popc(d);
+  const uint32_t ntop = n + (uint32_t)(31 - __clz((int)d)) - c;  // coefficients settled if c > 0
+  const uint32_t d0 = d >> 2, d1 = d0 & (d0 - 1), d2 = d1 & (d1 - 1), d3 = d2 & (d2 - 1), d4 = d3 & (d3 - 1);
+  r.ok = !((test && (term == 0 || tpos > left || (c != 0 && ntop > 32))) || d4 != 0 || n > 32);
+  const uint32_t y = d0 - (d1 >> 1) - (d2 >> 2) - (d3 >> 3);  // data bits moved down by 2 + rank
+  r.x = verb | shl32c(y, n);                                  // (n == 32 and ok imply y == 0)
+  const uint32_t used = test ? tpos : 0u;
+  r.dn = dn;
+  r.bits = left - used;
+  r.bp = bp + m + used;
+  r.n = c ? ntop : n;
+  return r;
+}
+
+template <int N>
+__device__ __forceinline__ bool decode_pair_narrow(ColReader& br, int kmin, int k, uint32_t& bits, uint32_t& n, int& lowest,
+                                                   bool& done, typename PlaneWord<N>::type* plane1, typename PlaneWord<N>::type* plane2)
+{
+  const bool dn1 = done || k - 1 < kmin || bits == 0;
+  const NarrowParse p1 = narrow_plane_parse(br, dn1, bits, br.bp, n);
+  const bool dn2 = dn1 || k - 2 < kmin || p1.bits == 0;
+  const NarrowParse p2 = narrow_plane_parse(br, dn2, p1.bits, p1.bp, p1.n);
+  if (__any_sync(0xffffffffu, !(p1.ok && p2.ok)))
+    return false;
+  if (!dn1)
+    *plane1 = (typename PlaneWord<N>::type)p1.x;
+  if (!dn2)
+    *plane2 = (typename PlaneWord<N>::type)p2.x;
+  done = dn2;
+  lowest = dn2 ? (dn1 ? lowest : k - 1) : k - 2;
+  bits = p2.bits;
+  br.bp = p2.bp;
+  n = p2.n;
+  return true;
+}
+
 template <int N>
 __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, int klo, int kbase, LockDecodeState& st,
                                                        typename PlaneWord<N>::type* sp)
@@ -1065,11 +1341,23 @@ __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, 
   int k = st.k, lowest = st.lowest;
   bool done = st.done;
   PlaneRec<N> rec = { 0, 0, 0, sp, false };
+  // blocks of 64 values: narrow steps while no block of the warp has more than 32 significant coefficients
+  // (n only grows, so once a pair has gone the general way with n > 32 somewhere the test is skipped)
+  bool narrow = N > 32 && ZB_NARROW;
   while (k > klo && __any_sync(FULL, !done)) {
     if (br.needs_restage()) {  // variable rate, long blocks: slide the window (positions in rec would go stale)
       finish_plane<N>(br, rec);
       rec.store = false;
       br.restage();
+    }
+    if constexpr (N > 32 && ZB_NARROW) {
+      if (narrow) {
+        if (decode_pair_narrow<N>(br, kmin, k, bits, n, lowest, done, sp + (k - 1 - kbase) * 32, sp + (k - 2 - kbase) * 32)) {
+          k -= 2;
+          continue;
+        }
+        narrow = !__any_sync(FULL, n > 32);  // (the general steps below may still find every lane narrow for the next pair)
+      }
     }
     decode_plane_lockstep<N>(br, kmin, k - 1, bits, n, lowest, done, sp + (k - 1 - kbase) * 32, rec);
     decode_plane_lockstep<N>(br, kmin, k - 2, bits, n, lowest, done, sp + (k - 2 - kbase) * 32, rec);
@@ -1081,6 +1369,88 @@ __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, 
   st.k = k;
   st.lowest = lowest;
   st.done = done;
+}
+
+// Run/event decoder for blocks of 64 values.  While few coefficients are significant most planes of
+// smooth data code as "n verbatim bits, then a lone '0' group test" (about two planes in three on the
+// benchmark field), and a run of such planes is a periodic bit pattern: the test bits sit at positions
+// n, 2n+1, 3n+2, ... of the stream.  Each lane therefore walks ITS OWN planes (k is per lane here,
+// not warp uniform): a step looks at 32 stream bits, finds the first test bit that is set with one
+// masked find-first-set against a table of test positions (ColReader::run_mask) - limited to the bits
+// the budget still covers and the planes left above the precision limit and the bottom of the resident
+// set -, stores the planes before it with a two-instruction extract each, and then parses the one
+// plane that follows with the general step (decode_plane_lockstep).  The warp iterates until every
+// lane has reached the bottom of the set: about 13 steps instead of 36 plane iterations at rate 8,
+// and the empty planes at the top of a block (n = 0) go thirty-two at a time.
+template <int N>
+__device__ __forceinline__ void decode_planes_events(ColReader& br, int kmin, int klo, int kbase, LockDecodeState& st,
+                                                     typename PlaneWord<N>::type* sp)
+{
+  using PW = typename PlaneWord<N>::type;
+  constexpr uint32_t FULL = 0xffffffffu;
+  uint32_t bits = st.bits, n = st.n;
+  int k = st.k, lowest = st.lowest;
+  bool done = st.done;
+  PlaneRec<N> rec = { 0, 0, 0, sp, false };
+  const int kfloor = klo > kmin ? klo : kmin;  // planes below are not coded (in this set / at all)
+  while (__any_sync(FULL, !done && k > klo)) {
+    if (br.needs_restage()) {  // variable rate, long blocks: slide the window (positions in rec would go stale)
+      finish_plane<N>(br, rec);
+      rec.store = false;
+      br.restage();
+    }
+    // (a) the run of planes whose group test fails at once
+    {
+      const bool active = !done && k > kfloor && n < 32;
+      const uint32_t w = br.peek32(br.bp);
+      const uint32_t L = n + 1;
+      const uint32_t span = (uint32_t)(k - kfloor) * L;               // bits the planes still to come would take
+      const uint32_t valid = active ? (br.run_mask(n & 31) & mask32(bits < span ? bits : span)) : 0u;
+      const uint32_t hit = w & valid;
+      const uint32_t j = (uint32_t)__popc(valid & ((hit & (0u - hit)) - 1u));  // test positions below the first set one
+      const uint32_t vm = mask32(n);
+      PW* dst = sp + (k - 1 - kbase) * 32;
+      uint32_t ww = w;
+      for (uint32_t i = 0; i < j; i++) {
+        *dst = (PW)(ww & vm);
+        dst -= 32;
+        ww = shr32c(ww, L);
+      }
+      br.bp += j * L;
+      bits -= j * L;
+      k -= (int)j;
+      lowest = j ? k : lowest;
+    }
+    // (b) the plane that follows, by the general step; lanes at the bottom of the set sit it out
+    {
+      bool d = done || k <= klo;
+      decode_plane_lockstep<N>(br, kmin, k - 1, bits, n, lowest, d, sp + (k - 1 - kbase) * 32, rec);
+      if (k > klo) {
+        done = d;
+        k -= d ? 0 : 1;
+      }
+    }
+  }
+  finish_plane<N>(br, rec);
+  st.bits = bits;
+  st.n = n;
+  st.k = k;
+  st.lowest = lowest;
+  st.done = done;
+}
+
+// developer switch for A/B timing: 0 keeps the plane-lockstep loop for blocks of 64 values
+#ifndef ZB_EVENTS
+#define ZB_EVENTS 0
+#endif
+template <int N>
+__device__ __forceinline__ void decode_planes_any(ColReader& br, int kmin, int klo, int kbase, LockDecodeState& st,
+                                                  typename PlaneWord<N>::type* sp)
+{
+  if constexpr (N > 32 && ZB_EVENTS)
+    decode_planes_events<N>(br, kmin, klo, kbase, st, sp);
+  else
+    decode_planes_lockstep<N>(br, kmin, klo, kbase, st, sp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1310,11 +1680,13 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
 
   UInt u[N];
   UInt any = 0;  // reversible mode: OR of all coefficients
+  // lossy modes: u holds q + 0xaaaa..., the XOR half of int2uint happens inside the plane transposes
+  constexpr int NEG = REV ? 0 : 1;
   if (!reversible) {
     xform_fwd<0, DIMS>(q);
 #pragma unroll
     for (int i = 0; i < N; i++)
-      u[i] = int2uint(q[perm_at<DIMS>(i)]);
+      u[i] = (UInt)q[perm_at<DIMS>(i)] + (UInt)0xaaaaaaaaaaaaaaaaull;
   }
   else {
     xform_fwd<2, DIMS>(q);
@@ -1361,8 +1733,8 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
       // blocks that stop within the high half (accuracy 1e-6, precision 32) are fastest with an
       // undivided half, blocks that go a few planes further (rate 8) with a 16-plane window.
       if (st.k > 32) {
-        to_planes_half<1, UInt, N>(u, sp);
-        encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp);
+        const int kup = to_planes_half<1, NEG, UInt, N>(u, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp, 32 + kup);
       }
 #pragma unroll 1
       for (int w = 1; w >= 0; w--) {
@@ -1370,29 +1742,29 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
           break;
         if (st.k <= 16 * w)
           continue;
-        to_planes_window<0>(u, sp, (uint32_t)w);
-        encode_planes_lockstep<N>(bw, limit, kmin, 16 * w, 16 * w, st, sp);
+        const int kup = to_planes_window<0, NEG>(u, sp, (uint32_t)w);
+        encode_planes_lockstep<N>(bw, limit, kmin, 16 * w, 16 * w, st, sp, 16 * w + kup);
       }
     }
     else if constexpr (P == 64) {
       if (st.k > 32) {
-        to_planes_half<1, UInt, N>(u, sp);
-        encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp);
+        const int kup = to_planes_half<1, NEG, UInt, N>(u, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp, 32 + kup);
       }
       if (__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < limit)) {
-        to_planes_half<0, UInt, N>(u, sp);
-        encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp);
+        const int kup = to_planes_half<0, NEG, UInt, N>(u, sp);
+        encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp, kup);
       }
     }
     else {
-      to_planes_half<0, UInt, N>(u, sp);
-      encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp);
+      const int kup = to_planes_half<0, NEG, UInt, N>(u, sp);
+      encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp, kup);
     }
     const uint32_t used = bw.tell() - start;
     bits += used < budget ? used : budget;
   }
   else if (coded) {
-    to_planes<UInt, N>(u, sp);
+    to_planes<NEG, UInt, N>(u, sp);
     bits += encode_planes<N, P>(bw, prm.maxbits - bits, maxprec, sp);
   }
   if (pad && bits < prm.minbits) {
@@ -1443,13 +1815,16 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   }
 
   UInt u[N];
+  // lossy modes: the plane transposes deliver u ^ 0xaaaa... (the XOR half of uint2int); planes that
+  // are never decoded leave the mask's bits
+  constexpr int NEG = REV ? 0 : 2;
   if constexpr (is_lockstep<Reader>::value) {
     const uint32_t budget = prm.maxbits - bits;
     const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
     LockDecodeState st = { budget, 0, P, P, zero };
 #pragma unroll
     for (int i = 0; i < N; i++)
-      u[i] = 0;
+      u[i] = (UInt)NegaWord<NEG>::w64;
     if constexpr (REV) {
       // mirror of the encoder's shortcut: leading '0' tests while no coefficient is significant are
       // empty planes; the warp skips the ones all its blocks have in common (even count, at most the
@@ -1468,42 +1843,43 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
       st.k = P - (int)skip;
     }
     if constexpr (P == 64 && N == 64) {
-      decode_planes_lockstep<N>(br, kmin, 32, 32, st, sp);
-      from_planes_half<1, UInt, N>(u, sp, st.lowest);
+      // (coefficients 32..63 are transposed only once some block of the warp has one of them significant)
+      decode_planes_any<N>(br, kmin, 32, 32, st, sp);
+      from_planes_half<1, NEG, UInt, N>(u, sp, st.lowest, __any_sync(0xffffffffu, st.n > 32));
       if (__any_sync(0xffffffffu, !st.done && st.k > kmin && st.bits != 0)) {
-        decode_planes_lockstep<N>(br, kmin, 16, 16, st, sp);
-        from_planes_window<1>(u, sp, st.lowest);
+        decode_planes_any<N>(br, kmin, 16, 16, st, sp);
+        from_planes_window<1, NEG>(u, sp, st.lowest, __any_sync(0xffffffffu, st.n > 32));
         if (__any_sync(0xffffffffu, !st.done && st.k > kmin && st.bits != 0)) {
-          decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);
-          from_planes_window<0>(u, sp, st.lowest);
+          decode_planes_any<N>(br, kmin, 0, 0, st, sp);
+          from_planes_window<0, NEG>(u, sp, st.lowest, __any_sync(0xffffffffu, st.n > 32));
         }
       }
       __syncthreads();  // the warps of the CTA enter the long straight-line tail together (shared instruction fetch)
     }
     else if constexpr (P == 64) {
       decode_planes_lockstep<N>(br, kmin, 32, 32, st, sp);
-      from_planes_half<1, UInt, N>(u, sp, st.lowest);
+      from_planes_half<1, NEG, UInt, N>(u, sp, st.lowest);
       if (__any_sync(0xffffffffu, !st.done && st.k > kmin && st.bits != 0)) {
         decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);
-        from_planes_half<0, UInt, N>(u, sp, st.lowest);
+        from_planes_half<0, NEG, UInt, N>(u, sp, st.lowest);
       }
       __syncthreads();
     }
     else {
-      decode_planes_lockstep<N>(br, kmin, 0, 0, st, sp);
-      from_planes_half<0, UInt, N>(u, sp, st.lowest);
+      decode_planes_any<N>(br, kmin, 0, 0, st, sp);
+      from_planes_half<0, NEG, UInt, N>(u, sp, st.lowest, N <= 32 || __any_sync(0xffffffffu, st.n > 32));
     }
     bits += budget - st.bits;
   }
   else if (!zero) {
     int kstop;
     bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
-    from_planes<UInt, N>(u, sp, kstop);
+    from_planes<NEG, UInt, N>(u, sp, kstop);
   }
   else {
 #pragma unroll
     for (int i = 0; i < N; i++)
-      u[i] = 0;
+      u[i] = (UInt)NegaWord<NEG>::w64;
   }
   if (zero)
     bits = 1;
@@ -1513,7 +1889,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   Int q[N];
 #pragma unroll
   for (int i = 0; i < N; i++)
-    q[perm_at<DIMS>(i)] = uint2int(u[i]);
+    q[perm_at<DIMS>(i)] = REV ? uint2int(u[i]) : (Int)(u[i] - (UInt)0xaaaaaaaaaaaaaaaaull);
   if (!reversible)
     xform_inv<1, DIMS>(q);
   else

@@ -560,6 +560,57 @@ zfp_bool zfp_stream_set_execution(zfp_stream* zfp, zfp_exec_policy policy)
   return zfp_true;
 }
 
+// OpenMP execution is the reference library's; as in a reference build without OpenMP the request
+// fails and the current policy stays (src/zfp.c:956-974 via zfp_stream_set_execution)
+zfp_bool zfp_stream_set_omp_threads(zfp_stream*, uint) { return zfp_false; }
+zfp_bool zfp_stream_set_omp_chunk_size(zfp_stream*, uint) { return zfp_false; }
+
+// mode configurations (src/zfp.c:466-533)
+zfp_config zfp_config_none(void)
+{
+  zfp_config c;
+  memset(&c, 0, sizeof(c));
+  c.mode = zfp_mode_null;
+  return c;
+}
+zfp_config zfp_config_rate(double rate, zfp_bool align)
+{
+  zfp_config c = zfp_config_none();
+  c.mode = zfp_mode_fixed_rate;
+  c.arg.rate = align ? -rate : +rate;
+  return c;
+}
+zfp_config zfp_config_precision(uint precision)
+{
+  zfp_config c = zfp_config_none();
+  c.mode = zfp_mode_fixed_precision;
+  c.arg.precision = precision;
+  return c;
+}
+zfp_config zfp_config_accuracy(double tolerance)
+{
+  zfp_config c = zfp_config_none();
+  c.mode = zfp_mode_fixed_accuracy;
+  c.arg.tolerance = tolerance;
+  return c;
+}
+zfp_config zfp_config_reversible(void)
+{
+  zfp_config c = zfp_config_none();
+  c.mode = zfp_mode_reversible;
+  return c;
+}
+zfp_config zfp_config_expert(uint minbits, uint maxbits, uint maxprec, int minexp)
+{
+  zfp_config c = zfp_config_none();
+  c.mode = zfp_mode_expert;
+  c.arg.expert.minbits = minbits;
+  c.arg.expert.maxbits = maxbits;
+  c.arg.expert.maxprec = maxprec;
+  c.arg.expert.minexp = minexp;
+  return c;
+}
+
 zfp_exec_params_cuda* zfp_stream_cuda_params(zfp_stream* zfp)
 {
   if (zfp->exec.policy != zfp_exec_cuda) return NULL;

@@ -93,7 +93,7 @@ cudaError_t run_decode_var(const DecodeArgs& a)
   if (e != cudaSuccess) return e;
   const uint64_t ctas = (a.b1 - a.b0 + threads - 1) / threads;
   kernel<<<(unsigned)ctas, threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
-                                                    static_cast<const uint32_t*>(a.in), a.offsets, a.lengths, a.b0, a.b1);
+                                                    static_cast<const uint32_t*>(a.in), a.offsets, a.lengths, a.b0, a.b1, a.check);
   return cudaGetLastError();
 }
 
@@ -151,7 +151,7 @@ cudaError_t run_decode(const DecodeArgs& a)
   if (e != cudaSuccess) return e;
   const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;
   kernel<<<(unsigned)ctas, kThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
-                                                    a.start_bit, a.offsets, a.b0, a.b1);
+                                                    a.start_bit, a.offsets, a.b0, a.b1, a.lengths, a.check);
   return cudaGetLastError();
 }
 
@@ -169,7 +169,7 @@ cudaError_t run_decode4(const DecodeArgs& a)
 {
   const unsigned ctas = (unsigned)((a.b1 - a.b0 + kThreads4 - 1) / kThreads4);
   decode4_kernel<TYPE, OFFS><<<ctas, kThreads4, 0, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
-                                                            a.start_bit, a.offsets, a.b0, a.b1);
+                                                            a.start_bit, a.offsets, a.b0, a.b1, a.lengths, a.check);
   return cudaGetLastError();
 }
 

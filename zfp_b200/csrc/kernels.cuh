@@ -243,9 +243,13 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   extern __shared__ uint64_t smem_raw[];
   const uint32_t words = prm.maxbits >> 5;  // 32-bit words per block (maxbits % 32 == 0)
   const uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (words + kStageSlack) * 32 * 4;
-  char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
-  PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
+  // (byte offsets kept opaque: left alone, the compiler re-derives them from the thread index inside the
+  // coder loops - a dozen instructions per iteration - rather than hold two registers across the transform)
+  uint32_t sp_off = (threadIdx.x >> 5) * warp_bytes + (threadIdx.x & 31) * (uint32_t)sizeof(PW);
+  uint32_t stage_off = (threadIdx.x >> 5) * warp_bytes + kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (threadIdx.x & 31) * 4u;
+  asm volatile("" : "+r"(sp_off), "+r"(stage_off));
+  PW* sp = reinterpret_cast<PW*>(reinterpret_cast<char*>(smem_raw) + sp_off);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + stage_off);
 
   // no early exit: lanes past the end redo the last block and discard it, so that warp-wide votes
   // inside encode_block always see 32 lanes
@@ -291,9 +295,12 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 // per CTA and rendezvous once after the stream parse: their tail (inverse transposes, lifting, cast)
 // is ~50 KB of straight-line code, far more than the 32 KB instruction cache level, and warps that
 // walk it together share the fetches (measured 512^3 fp64 rate 8: 0.90 -> 0.81 ms).
+#ifndef ZB_DEC64_THREADS
+#define ZB_DEC64_THREADS 192
+#endif
 template <int TYPE> struct DecCfg {
-  static constexpr int threads = Traits<TYPE>::P == 64 ? 192 : kThreads;
-  static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 2 : (rev ? 6 : 9); }
+  static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_DEC64_THREADS : kThreads;
+  static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? 6 : 9); }
 };
 constexpr int kReadSlack = 5;  // zero words after the block: a plane's reads reach 64 + 32 bits past the position, rounded up to words
 
@@ -306,11 +313,19 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   constexpr int N = 1 << (2 * DIMS);
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
+  __shared__ uint32_t run_table[32];  // test-bit positions of the run decoder (ColReader::run_mask)
+  if (threadIdx.x < 32)
+    ColReader::fill_run_table(run_table, threadIdx.x);
+  __syncthreads();
   const uint32_t words = prm.maxbits >> 5;
   const uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (words + kReadSlack) * 32 * 4;
-  char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
-  PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
+  // (byte offsets kept opaque: left alone, the compiler re-derives them from the thread index inside the
+  // coder loops - a dozen instructions per iteration - rather than hold two registers across the transform)
+  uint32_t sp_off = (threadIdx.x >> 5) * warp_bytes + (threadIdx.x & 31) * (uint32_t)sizeof(PW);
+  uint32_t stage_off = (threadIdx.x >> 5) * warp_bytes + kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (threadIdx.x & 31) * 4u;
+  asm volatile("" : "+r"(sp_off), "+r"(stage_off));
+  PW* sp = reinterpret_cast<PW*>(reinterpret_cast<char*>(smem_raw) + sp_off);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + stage_off);
 
   const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;  // no early exit (warp-wide votes in decode_block)
@@ -346,6 +361,7 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
 
   ColReader br;
   br.init(stage);
+  br.set_run_table(run_table);
   typename TR::Scalar v[N];
   decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
   if (valid) {
@@ -372,9 +388,13 @@ encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
   constexpr uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + kVarStageWords * 32 * 4;
-  char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
-  PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
+  // (byte offsets kept opaque: left alone, the compiler re-derives them from the thread index inside the
+  // coder loops - a dozen instructions per iteration - rather than hold two registers across the transform)
+  uint32_t sp_off = (threadIdx.x >> 5) * warp_bytes + (threadIdx.x & 31) * (uint32_t)sizeof(PW);
+  uint32_t stage_off = (threadIdx.x >> 5) * warp_bytes + kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (threadIdx.x & 31) * 4u;
+  asm volatile("" : "+r"(sp_off), "+r"(stage_off));
+  PW* sp = reinterpret_cast<PW*>(reinterpret_cast<char*>(smem_raw) + sp_off);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + stage_off);
 
   const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * EncCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;
@@ -395,16 +415,25 @@ encode_var_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g
 template <int TYPE, int DIMS, bool REV>
 __global__ void __launch_bounds__(DecCfg<TYPE>::threads, DecCfg<TYPE>::min_ctas(REV))
 decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm, const uint32_t* __restrict__ in,
-                  const uint64_t* __restrict__ offsets, const uint16_t* __restrict__ lengths, uint64_t block0, uint64_t block1)
+                  const uint64_t* __restrict__ offsets, const uint16_t* __restrict__ lengths, uint64_t block0, uint64_t block1,
+                  uint32_t* __restrict__ check)
 {
   using TR = Traits<TYPE>;
   constexpr int N = 1 << (2 * DIMS);
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
+  __shared__ uint32_t run_table[32];  // test-bit positions of the run decoder (ColReader::run_mask)
+  if (threadIdx.x < 32)
+    ColReader::fill_run_table(run_table, threadIdx.x);
+  __syncthreads();
   constexpr uint32_t warp_bytes = kStagedPlanes * 32 * (uint32_t)sizeof(PW) + kVarStageWords * 32 * 4;
-  char* base = reinterpret_cast<char*>(smem_raw) + (threadIdx.x >> 5) * warp_bytes;
-  PW* sp = reinterpret_cast<PW*>(base) + (threadIdx.x & 31);
-  uint32_t* stage = reinterpret_cast<uint32_t*>(base + kStagedPlanes * 32 * sizeof(PW)) + (threadIdx.x & 31);
+  // (byte offsets kept opaque: left alone, the compiler re-derives them from the thread index inside the
+  // coder loops - a dozen instructions per iteration - rather than hold two registers across the transform)
+  uint32_t sp_off = (threadIdx.x >> 5) * warp_bytes + (threadIdx.x & 31) * (uint32_t)sizeof(PW);
+  uint32_t stage_off = (threadIdx.x >> 5) * warp_bytes + kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (threadIdx.x & 31) * 4u;
+  asm volatile("" : "+r"(sp_off), "+r"(stage_off));
+  PW* sp = reinterpret_cast<PW*>(reinterpret_cast<char*>(smem_raw) + sp_off);
+  uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + stage_off);
 
   const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;
@@ -413,8 +442,12 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
   const uint32_t phase = (uint32_t)(off & 31), len = lengths[b];
   ColReader br;
   br.init_var(stage, kVarStageWords, in + (off >> 5), (phase + len + 31) >> 5, phase);
+  br.set_run_table(run_table);
   typename TR::Scalar v[N];
-  decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  const uint32_t bits = decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  // the index the offsets came from must describe THIS stream: its length against the parsed one
+  if (check && bits != len)
+    atomicOr(check, 1u);
   if (valid) {
     const BlockPos<DIMS> pos = locate<DIMS>(g, b);
     scatter<DIMS>(v, data, g, pos);
@@ -426,7 +459,7 @@ template <int TYPE, int DIMS, int OFFS, bool REV>
 __global__ void __launch_bounds__(kThreads)
 decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
               const void* __restrict__ in, uint64_t start_bit, const uint64_t* __restrict__ offsets, uint64_t block0,
-              uint64_t block1)
+              uint64_t block1, const uint16_t* __restrict__ lengths, uint32_t* __restrict__ check)
 {
   using TR = Traits<TYPE>;
   constexpr int N = 1 << (2 * DIMS);
@@ -440,7 +473,9 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   BitReader br;
   br.init(in, OFFS ? offsets[b] : start_bit + b * (uint64_t)prm.maxbits);
   typename TR::Scalar v[N];
-  decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  const uint32_t bits = decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  if (OFFS == 1 && check && lengths && bits != lengths[b])
+    atomicOr(check, 1u);
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
   scatter<DIMS>(v, data, g, pos);
 }

@@ -335,7 +335,8 @@ encode4_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
 template <int TYPE, int OFFS>
 __global__ void __launch_bounds__(kThreads4)
 decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm, const void* __restrict__ in,
-               uint64_t start_bit, const uint64_t* __restrict__ offsets, uint64_t block0, uint64_t block1)
+               uint64_t start_bit, const uint64_t* __restrict__ offsets, uint64_t block0, uint64_t block1,
+               const uint16_t* __restrict__ lengths, uint32_t* __restrict__ check)
 {
   using TR = Traits<TYPE>;
   using Scalar = typename TR::Scalar;
@@ -383,7 +384,7 @@ decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params 
       maxprec = (uint32_t)br.get(TR::PBITS) + 1;
       bits += TR::PBITS;
     }
-    decode_planes4<P>(br, prm.maxbits - bits, maxprec, pl);
+    bits += decode_planes4<P>(br, prm.maxbits - bits, maxprec, pl);
     from_planes4(u, pl);
     for (int i = 0; i < 256; i++)
       q[c_perm4[i]] = uint2int(u[i]);
@@ -406,6 +407,13 @@ decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params 
     else
       for (int i = 0; i < 256; i++)
         v[i] = (Scalar)q[i];
+  }
+  if constexpr (OFFS == 1) {
+    // the index the offsets came from must describe THIS stream: compare its length with the parsed one
+    if (zero) bits = 1;
+    if (bits < prm.minbits) bits = prm.minbits;
+    if (check && lengths && bits != lengths[b])
+      atomicOr(check, 1u);
   }
   scatter4(v, data, g, locate4(g, b));
 }

@@ -50,6 +50,7 @@ struct DecodeArgs {
   cudaStream_t st;
   int staged;       // OFFS 0 only: use the shared-memory staged fast path when the stream is word aligned
   uint64_t b0, b1;  // block range [b0, b1) to decode (random access); the whole field is [0, nblocks)
+  uint32_t* check;  // OFFS 1: set to non-zero by any block whose parsed length differs from lengths[b] (nullptr: no check)
 };
 
 // one translation unit per scalar type and direction (inst_*.cu) defines these
