@@ -7,6 +7,8 @@
 
 #include "kernels.cuh"
 #include "kernels4d.cuh"
+#include "kernels_ws.cuh"
+#include "kernels_q4.cuh"
 
 namespace zb {
 
@@ -45,10 +47,17 @@ inline cudaError_t allow_smem_cached(K kernel, size_t bytes, size_t (&granted)[6
 }
 
 
+template <int TYPE> cudaError_t run_encode_q4(const EncodeArgs& a);
+
 template <int TYPE, int DIMS, bool REV>
 cudaError_t run_encode_staged(const EncodeArgs& a)
 {
   constexpr int N = 1 << (2 * DIMS);
+  if constexpr (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) {
+    static const bool q4 = getenv("ZFP_B200_Q4") != nullptr;
+    if (q4 && (a.prm.maxbits & 63) == 0 && (a.start_bit & 63) == 0)
+      return run_encode_q4<TYPE>(a);
+  }
   auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
   constexpr int threads = EncCfg<TYPE>::threads;
   const size_t smem = (size_t)(threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
@@ -118,10 +127,75 @@ cudaError_t run_encode(const EncodeArgs& a)
   return cudaGetLastError();
 }
 
+// multiprocessors of the current device
+inline int device_sms()
+{
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;
+  return n;
+}
+
+// warp-specialised decoder (kernels_ws.cuh): persistent CTAs, two per multiprocessor
+template <int TYPE>
+cudaError_t run_decode_ws(const DecodeArgs& a)
+{
+  auto kernel = decode_ws_kernel<TYPE>;
+  const size_t smem = ws_cta_bytes(a.prm.maxbits >> 5);
+  static size_t granted[64] = { 0 };
+  cudaError_t e = allow_smem_cached(kernel, smem, granted);
+  if (e != cudaSuccess) return e;
+  const uint64_t nbatches = (a.b1 - a.b0 + 31) / 32;
+  uint64_t ctas = (nbatches + kWsPairs - 1) / kWsPairs;
+  const uint64_t resident = (uint64_t)device_sms() * 2;
+  if (ctas > resident) ctas = resident;
+  kernel<<<(unsigned)ctas, kWsThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                      static_cast<const uint64_t*>(a.in), a.start_bit, a.b0, a.b1);
+  return cudaGetLastError();
+}
+
+// four-lanes-per-block encoder (kernels_q4.cuh)
+template <int TYPE>
+cudaError_t run_encode_q4(const EncodeArgs& a)
+{
+  auto kernel = encode_q4_kernel<TYPE>;
+  const size_t smem = (size_t)(kQ4Threads / 32) * q4_warp_bytes(a.prm.maxbits >> 5);
+  static size_t granted[64] = { 0 };
+  cudaError_t e = allow_smem_cached(kernel, smem, granted);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (a.g.nblocks + kQ4Threads - 1) / kQ4Threads;
+  kernel<<<(unsigned)ctas, kQ4Threads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                      static_cast<uint64_t*>(a.out), a.start_bit);
+  return cudaGetLastError();
+}
+
+// four-lanes-per-block decoder (kernels_q4.cuh)
+template <int TYPE>
+cudaError_t run_decode_q4(const DecodeArgs& a)
+{
+  auto kernel = decode_q4_kernel<TYPE>;
+  const size_t smem = (size_t)(kQ4Threads / 32) * q4_warp_bytes(a.prm.maxbits >> 5);
+  static size_t granted[64] = { 0 };
+  cudaError_t e = allow_smem_cached(kernel, smem, granted);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (a.b1 - a.b0 + kQ4Threads - 1) / kQ4Threads;
+  kernel<<<(unsigned)ctas, kQ4Threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                      static_cast<const uint64_t*>(a.in), a.start_bit, a.b0, a.b1);
+  return cudaGetLastError();
+}
+
 template <int TYPE, int DIMS, bool REV>
 cudaError_t run_decode_staged(const DecodeArgs& a)
 {
   constexpr int N = 1 << (2 * DIMS);
+  if constexpr (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) {
+    static const bool q4 = getenv("ZFP_B200_Q4") != nullptr;
+    if (q4 && (kQ4Threads / 32) * q4_warp_bytes(a.prm.maxbits >> 5) <= 200 * 1024)
+      return run_decode_q4<TYPE>(a);
+    static const bool ws = getenv("ZFP_B200_WS") != nullptr && ws_cta_bytes(4096 >> 5) > 0;
+    if (ws && ws_cta_bytes(a.prm.maxbits >> 5) <= 110 * 1024)
+      return run_decode_ws<TYPE>(a);
+  }
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
   const size_t smem = (size_t)(DecCfg<TYPE>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4);
