@@ -8,6 +8,18 @@ slowest dimension, one per rank, no data-path collective (fixed-rate slabs sit a
 offsets) -> weak scaling.
 
 metric = (uncompressed bytes compressed + uncompressed bytes decompressed) / time, GB = 1e9 B.
+(`roundtrip_gbs` = uncompressed bytes of ONE array / step time is printed beside it.)
+
+Extra keys of the line (all measured in this run):
+  variable_rate   second timed leg on every N: the same slab at fixed accuracy 1e-6 - encode, exchange of the
+                  slab bit lengths (all_gather, stream ordered: no host round trip), device prefix, decode -
+                  with the slab bit lengths and a check that the slabs tile the global stream
+  multi_gpu_parity (N >= 2) a small field compressed as N slabs and assembled over NCCL equals the stream ONE
+                  GPU produces for the whole field (fixed rate and fixed accuracy)
+  other_configs   (N == 1) the other BASELINE.json configurations that fit one GPU, compress / decompress ms and
+                  fraction of the measured HBM peak
+  ref_cuda        (N == 1) the backend this project replaces (reference src/cuda_zfp, unmodified, built for
+                  sm_100 by oracle/Makefile) timed on the same device-resident 1024^3 field, streams compared
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -31,7 +43,8 @@ METRIC = "compress+decompress GB/s (uncompressed), 3D fp64 fixed-rate"
 UNIT = "GB/s"
 RATE = 8
 SIDE = 1024          # per-GPU slab is SIDE^3 values (8 GiB fp64)
-CPU_SIDE = 512       # bounded CPU sample: CPU_SIDE^3 sub-box of the same field (1 GiB)
+CPU_SIDE = 512       # bounded CPU sample of the in-run cpu_baseline leg: CPU_SIDE^3 sub-box of the same field (1 GiB)
+VAR_MODE = {"accuracy": 1e-6}
 
 
 def peaks():
@@ -176,28 +189,246 @@ def time_reference(a, steps, warmup, threads):
     return tc, td, words, out
 
 
+def host_field(side):
+    """The bench field (rank 0's slab of field_slab) on the host, generated in chunks with torch CPU kernels."""
+    import torch
+    out = torch.empty((side, SIDE, SIDE), dtype=torch.float64)
+    g = torch.arange(SIDE, dtype=torch.float64) / (SIDE - 1)
+    y, x = g[None, :, None], g[None, None, :]
+    for z0 in range(0, side, 32):
+        z = g[z0:z0 + 32, None, None]
+        out[z0:z0 + 32] = torch.sin(2 * np.pi * (3 * x + 0.5 * y)) * torch.cos(4 * np.pi * z) + 0.25 * torch.sin(14 * np.pi * x * y * z)
+    return out.numpy()
+
+
 def run_reference(args):
+    """The reference's own CPU implementation on the box's host cores, SAME configuration as our arm: the full
+    1024^3 fp64 slab at rate 8 per step (zfp_exec_omp compress with all threads + serial decompress - upstream
+    has no parallel decompress, src/zfp.c:1137-1138).  Falls back to a 512^3 sub-box, and says so, only when
+    the host cannot hold the 17 GiB of buffers."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    a = cpu_sample_field(CPU_SIDE)
+    side = SIDE
+    try:
+        import psutil
+        if psutil.virtual_memory().available < 22 * 2 ** 30:
+            side = CPU_SIDE
+    except Exception:
+        pass
+    if args.quick:
+        side = 256
+    a = host_field(side) if side == SIDE else cpu_sample_field(side)
     tc, td, _, _ = time_reference(a, args.steps, args.warmup, threads)
     step = float(np.sum(tc) + np.sum(td)) / args.steps
     value = 2 * a.nbytes / step / 1e9
+    same = side == SIDE
+    workload = "3D fp64 %d^3 per GPU, fixed-rate %d, compress+decompress" % (SIDE, RATE)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D fp64 %d^3 per GPU, fixed-rate %d, compress+decompress" % (SIDE, RATE),
-                   "sample": "%d^3 sub-box of the same analytic field per step" % CPU_SIDE},
+        "dtype": "f64", "data": "synthetic", "roundtrip_gbs": a.nbytes / step / 1e9,
+        "config": {"workload": workload,
+                   "sample": "the full %d^3 slab per step (same configuration as the GPU arm)" % SIDE if same else
+                             "%d^3 sub-box of the same analytic field per step (host memory too small for the full slab)" % side},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": "%d^3 fp64 sub-box (%.2f GiB) per step; zfp_exec_omp compress with %d threads (%.3f GB/s) + serial decompress (%.3f GB/s; reference has no parallel decompress)"
-                                   % (CPU_SIDE, a.nbytes / 2 ** 30, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9)},
+                         "sample": "%d x %d x %d fp64 (%.2f GiB) per step; zfp_exec_omp compress with %d threads (%.3f GB/s) + serial decompress (%.3f GB/s; reference has no parallel decompress)"
+                                   % (a.shape[0], a.shape[1], a.shape[2], a.nbytes / 2 ** 30, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# extra legs of our arm
+# ---------------------------------------------------------------------------------------------------
+def variable_rate_leg(torch, dist, zb, x, y, rank, world, steps, warmup, barrier):
+    """Fixed accuracy 1e-6 on the same slab: encode -> all_gather of the slab bit lengths -> device prefix ->
+    decode, everything enqueued on one stream (zfp_b200/distributed.py DeviceSlab); the host synchronises only
+    at the ends of the timed region."""
+    from zfp_b200.distributed import DeviceSlab
+    dev = x.device
+    slab = DeviceSlab(tuple(x.shape), x.dtype, VAR_MODE, rank, world)
+    for _ in range(max(warmup, 3)):
+        slab.compress(x)
+        slab.decompress(y)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    launches0 = zb.launch_count()
+    ev[0].record()
+    for i in range(steps):
+        slab.compress(x)
+        ev[2 * i + 1].record()
+        slab.decompress(y)
+        ev[2 * i + 2].record()
+    barrier()
+    launches = zb.launch_count() - launches0
+    total = ev[0].elapsed_time(ev[-1])
+    enc = float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)]))
+    dec = float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)]))
+    t = torch.tensor([total, enc, dec], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total, enc, dec = [float(v) for v in t.tolist()]
+    # the slabs tile the global stream: every rank's base is the sum of the lower ranks' lengths
+    bases = torch.zeros(world, dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_gather_into_tensor(bases, slab.base)
+    else:
+        bases.copy_(slab.base)
+    lengths = [int(v) for v in slab.lengths.tolist()]
+    bases = [int(v) for v in bases.tolist()]
+    tiles = all(bases[r] == sum(lengths[:r]) for r in range(world)) and all(v > 0 for v in lengths)
+    # the decoded slab honours the tolerance
+    err = float((y - x).abs().max().item())
+    index_ok = int(slab.status.item()) == 0
+    raw = x.numel() * x.element_size()
+    out = {"mode": "fixed accuracy 1e-6", "ms_per_step": total / steps, "compress_ms": enc, "decompress_ms": dec,
+           "value": 2 * raw * world / (total / steps * 1e-3) / 1e9, "unit": UNIT, "slab_bits": lengths, "slab_base_bits": bases,
+           "slabs_tile_the_stream": bool(tiles), "max_abs_error": err, "within_tolerance": bool(err <= VAR_MODE["accuracy"]), "index_check_clean": bool(index_ok),
+           "compression_ratio": raw * 8.0 / max(1, lengths[rank]), "gpu_launches": launches,
+           "exchange": "all_gather_into_tensor of one int64 per rank on the compute stream, prefix + placement on the device (zfp_b200_bitcopy_ranked); no host synchronisation inside a step" if world > 1 else "single rank: no exchange"}
+    slab.close()
+    return out
+
+
+def multi_gpu_parity(torch, dist, zb, rank, world, dev):
+    """A small field compressed as `world` slabs, assembled into one stream over NCCL, against the stream ONE
+    GPU produces for the whole field.  Fixed rate (deterministic offsets) and fixed accuracy (exchanged lengths)."""
+    from zfp_b200.distributed import DeviceSlab, plan_slabs
+    shape = (16 * world + 8, 52, 60)
+    g = [torch.arange(n, device=dev, dtype=torch.float64) / (n - 1) for n in shape]
+    whole = torch.sin(5 * g[0][:, None, None] + 3 * g[1][None, :, None]) * torch.cos(4 * g[2][None, None, :]) + 0.1 * g[0][:, None, None] ** 2
+    plan = plan_slabs(shape, world)[rank]
+    mine = whole[plan.z0:plan.z1].contiguous()
+    ok = True
+    for mode in ({"rate": 8}, {"accuracy": 1e-5}):
+        ref = zb.compress(whole, **mode)
+        nwords = ref.nbytes // 8
+        out = torch.zeros(nwords + 2, dtype=torch.int64, device=dev)
+        slab = DeviceSlab(tuple(mine.shape), mine.dtype, mode, rank, world)
+        slab.compress(mine, global_words=out)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM)  # slabs are disjoint bit ranges of a zeroed buffer: sum == bitwise or
+        ok = ok and bool(torch.equal(out[:nwords], ref.words[:nwords].view(torch.int64)))
+        back = torch.empty_like(mine)
+        slab.decompress(back)
+        ok = ok and bool(torch.equal(back, zb.decompress(ref)[plan.z0:plan.z1]))
+        slab.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def time_pair(torch, zb, x, mode, reps=5):
+    c = zb.compress(x, **mode)
+    y = torch.empty_like(x)
+    zb.decompress(c, out=y)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tc = td = 0.0
+    for _ in range(reps):
+        e[0].record()
+        c = zb.compress(x, reuse=c, **mode)
+        e[1].record()
+        zb.decompress(c, out=y)
+        e[2].record()
+        torch.cuda.synchronize()
+        tc += e[0].elapsed_time(e[1]) / reps
+        td += e[1].elapsed_time(e[2]) / reps
+    return tc, td, c.nbytes
+
+
+def other_configs(torch, zb, dev, peak):
+    """BASELINE.json configurations besides the headline that fit one GPU (device-resident, same analytic
+    field family): compress / decompress time and fraction of the measured HBM peak (uncompressed + compressed
+    bytes over the time of the call)."""
+    def field(shape, dtype):
+        g = [torch.arange(n, device=dev, dtype=torch.float64) / (n - 1) for n in shape]
+        if len(shape) == 3:
+            z, y, x = g[0][:, None, None], g[1][None, :, None], g[2][None, None, :]
+            f = torch.empty(shape, dtype=torch.float64, device=dev)
+            for z0 in range(0, shape[0], 64):
+                zz = z[z0:z0 + 64]
+                f[z0:z0 + 64] = torch.sin(2 * np.pi * (3 * x + 0.5 * y)) * torch.cos(4 * np.pi * zz) + 0.25 * torch.sin(14 * np.pi * x * y * zz)
+        elif len(shape) == 2:
+            y, x = g[0][:, None], g[1][None, :]
+            f = torch.sin(2 * np.pi * (3 * x + 0.5 * y)) + 0.25 * torch.sin(14 * np.pi * x * y)
+        else:
+            w, z, y, x = g[0][:, None, None, None], g[1][None, :, None, None], g[2][None, None, :, None], g[3][None, None, None, :]
+            f = torch.sin(2 * np.pi * (x + 0.5 * y)) * torch.cos(3 * np.pi * z) + 0.25 * torch.sin(5 * np.pi * w * x)
+        return (torch.round(f * 2 ** 20) if dtype in (torch.int32, torch.int64) else f).to(dtype)
+
+    cases = [("3D fp64 1024^3 rate 4", (SIDE, SIDE, SIDE), torch.float64, {"rate": 4}),
+             ("3D fp64 1024^3 rate 16", (SIDE, SIDE, SIDE), torch.float64, {"rate": 16}),
+             ("3D fp64 1024^3 precision 32", (SIDE, SIDE, SIDE), torch.float64, {"precision": 32}),
+             ("3D fp32 1024^3 rate 8", (SIDE, SIDE, SIDE), torch.float32, {"rate": 8}),
+             ("2D fp32 16384^2 rate 8", (16384, 16384), torch.float32, {"rate": 8}),
+             ("4D fp64 64^4 rate 8", (64, 64, 64, 64), torch.float64, {"rate": 8}),
+             ("3D int32 1024^3 reversible", (SIDE, SIDE, SIDE), torch.int32, {"reversible": True})]
+    out, cached = {}, (None, None, None)
+    for name, shape, dtype, mode in cases:
+        try:
+            if cached[0] != (shape, dtype):
+                cached = (None, None, None)
+                torch.cuda.empty_cache()
+                cached = ((shape, dtype), field(shape, dtype), None)
+            x = cached[1]
+            tc, td, nbytes = time_pair(torch, zb, x, mode, reps=3)
+            raw = x.numel() * x.element_size()
+            out[name] = {"compress_ms": round(tc, 3), "decompress_ms": round(td, 3), "ratio": round(raw / nbytes, 2),
+                         "compress_hbm_frac": round((raw + nbytes) / (tc * 1e-3) / 1e9 / peak, 3),
+                         "decompress_hbm_frac": round((raw + nbytes) / (td * 1e-3) / 1e9 / peak, 3)}
+        except Exception as ex:  # report, never fake
+            out[name] = {"error": repr(ex)[:160]}
+    cached = None
+    torch.cuda.empty_cache()
+    return out
+
+
+def ref_cuda_leg(torch, zb, x, ours_stream_words, ours_nbytes):
+    """The backend this project replaces - reference src/cuda_zfp, unmodified, compiled for sm_100 into
+    oracle/_ref/libzfp_ref_cudaorig.so - on the same device-resident slab at rate 8 through the reference's
+    own zfp_compress / zfp_decompress under zfp_exec_cuda; its stream must equal ours."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libzfp_ref_cudaorig.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libzfp_ref_cudaorig.so not built"}
+    from oracle.oracle import Reference, ZFP_TYPE
+    R = Reference(so)
+    L = R.L
+    n = tuple(reversed(x.shape)) + (0,)
+    words = torch.zeros(ours_nbytes // 8 + 16, dtype=torch.int64, device=x.device)
+    y = torch.empty_like(x)
+    f, dims = R._field(x.data_ptr(), np.float64, n, None)
+    z = L.zfp_stream_open(None)
+    L.zfp_stream_set_rate(z, float(RATE), ZFP_TYPE[np.dtype(np.float64)], dims, 0)
+    bs = L.stream_open(words.data_ptr(), words.numel() * 8)
+    L.zfp_stream_set_bit_stream(z, bs)
+    if not L.zfp_stream_set_execution(z, 2):
+        return {"unavailable": "reference library built without CUDA"}
+
+    def run(fn, ptr, reps=3):
+        L.zfp_field_set_pointer(f, ptr)
+        L.zfp_stream_rewind(z)
+        nb = fn(z, f)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            L.zfp_stream_rewind(z)
+            fn(z, f)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, nb
+
+    tc, nbytes = run(L.zfp_compress, x.data_ptr())
+    same = bool(nbytes == ours_nbytes and torch.equal(words[: nbytes // 8], ours_stream_words[: nbytes // 8].view(torch.int64)))
+    td, _ = run(L.zfp_decompress, y.data_ptr())
+    raw = x.numel() * 8
+    L.zfp_field_free(f); L.zfp_stream_close(z); L.stream_close(bs)
+    return {"compress_ms": tc, "decompress_ms": td, "value": 2 * raw / ((tc + td) * 1e-3) / 1e9, "unit": UNIT,
+            "stream_identical_to_ours": same, "what": "reference src/cuda_zfp (unmodified) built for sm_100, zfp_exec_cuda, same device-resident slab"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -328,6 +559,18 @@ def run_ours(args):
     except Exception as ex:  # report, never fake
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)[:200]}
 
+    # ---- second timed leg: variable rate with the stream-ordered slab-length exchange (every rank)
+    try:
+        var = variable_rate_leg(torch, dist, zb, x, y, rank, world, args.steps, args.warmup, barrier)
+    except Exception as ex:  # report, never fake
+        var = {"error": repr(ex)[:300]}
+    parity_multi = None
+    if world > 1:
+        try:
+            parity_multi = multi_gpu_parity(torch, dist, zb, rank, world, dev)
+        except Exception as ex:
+            parity_multi = "error: " + repr(ex)[:200]
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,11 +602,22 @@ def run_ours(args):
                                % (nz, ny, nx, nz * world, ny, nx, RATE),
                    "parallelism": "slab-per-GPU x%d, no collective" % world,
                    "l2": "inputs (8 GiB) and outputs exceed the 126 MB L2; no explicit flush"},
+        "roundtrip_gbs": raw_bytes * world / (ms_per_step * 1e-3) / 1e9,
         "compress_gbs": raw_bytes * world / (enc_ms * 1e-3) / 1e9, "decompress_gbs": raw_bytes * world / (dec_ms * 1e-3) / 1e9,
         "compressed_bytes_per_gpu": comp_bytes,
         "roofline": dominant, "roofline_encode": roof_enc, "roofline_decode": roof_dec,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "variable_rate": var,
     }
+    if parity_multi is not None:
+        line["multi_gpu_parity"] = parity_multi
+    if world == 1 and not args.quick:
+        try:
+            line["ref_cuda"] = ref_cuda_leg(torch, zb, x, c.words, comp_bytes)
+            if line["ref_cuda"].get("value"):
+                line["ref_cuda"]["ours_over_ref_cuda"] = value / line["ref_cuda"]["value"]
+        except Exception as ex:
+            line["ref_cuda"] = {"error": repr(ex)[:200]}
 
     # ---- CPU baseline on this box's host cores (N=1 only), bounded sample, plus a parity check on it
     if world == 1 and not args.no_cpu:
@@ -383,6 +637,14 @@ def run_ours(args):
                 "stream_and_array_bit_identical_to_gpu": bool(parity)}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "error": repr(ex)[:200]}
+    if world == 1 and not args.quick and not args.no_others:
+        prev[0] = c = None
+        del x, y, words
+        torch.cuda.empty_cache()
+        try:
+            line["other_configs"] = other_configs(torch, zb, dev, peak)
+        except Exception as ex:
+            line["other_configs"] = {"error": repr(ex)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -395,7 +657,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--quick", action="store_true", help="smaller CPU sample")
+    ap.add_argument("--quick", action="store_true", help="smaller CPU sample, no ref_cuda / other_configs legs")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -78,11 +78,24 @@ enum {
 int zfp_b200_encode(const zfp_b200_desc* desc, const void* d_data, void* d_words, uint64 start_bit,
                     uint64* end_bit, zfp_b200_index* index, void* cuda_stream);
 
+/* Stream-ordered variant: the end position goes to DEVICE memory (*d_end_bit) and the call never
+ * synchronises cuda_stream, also for variable-rate parameters.  This is what the multi-GPU slab path
+ * uses: encode, exchange the slab lengths (ncclAllGather on the same stream) and place the slab
+ * (zfp_b200_bitcopy_ranked) without a host round trip. */
+int zfp_b200_encode_async(const zfp_b200_desc* desc, const void* d_data, void* d_words, uint64 start_bit,
+                          uint64* d_end_bit, zfp_b200_index* index, void* cuda_stream);
+
 /* Decode; mirror of the above.  index may be NULL for fixed-rate parameters.  For variable-rate
  * parameters a NULL index makes the backend rebuild one by scanning the stream (slow, sequential
  * in the stream order by the nature of the format). */
 int zfp_b200_decode(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
                     uint64* end_bit, const zfp_b200_index* index, void* cuda_stream);
+
+/* Stream-ordered decode: never synchronises cuda_stream.  Variable-rate parameters need the index of
+ * this stream; *d_status (device memory, zeroed by the caller) becomes non-zero if some block does not parse
+ * to the length the index records for it - the decoded array is then not to be trusted. */
+int zfp_b200_decode_async(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
+                          const zfp_b200_index* index, unsigned int* d_status, void* cuda_stream);
 
 /* Random access: decode only blocks [block0, block1) of the stream (stream order, x fastest:
  * b = bx + BX*(by + BY*(bz + BZ*bw)), src/template/ompcompress.c:168-198) into their places in the
@@ -93,11 +106,27 @@ int zfp_b200_decode(const zfp_b200_desc* desc, void* d_data, const void* d_words
 int zfp_b200_decode_blocks(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
                            uint64 block0, uint64 block1, const zfp_b200_index* index, void* cuda_stream);
 
+/* Random access by coordinates: decode, in ONE launch, every block that intersects the box
+ * lo[i] <= index_i < hi[i] (i = 0 is x, like desc->n; entries beyond desc->dims are ignored) into its place in
+ * the field at d_data.  Blocks are decoded whole, so up to 3 positions outside the box along each dimension are
+ * written too.  (The reference offers this only one block at a time through its C++ array classes,
+ * include/zfp/index.hpp:160-315.) */
+int zfp_b200_decode_box(const zfp_b200_desc* desc, void* d_data, const void* d_words, uint64 start_bit,
+                        const size_t* lo, const size_t* hi, const zfp_b200_index* index, void* cuda_stream);
+
 /* Bit-granular device copy dst[dst_bit, dst_bit+nbits) = src[src_bit, ...): places a slab stream
  * produced at another bit phase / on another GPU into a global stream.  Destination words fully
  * inside the range are overwritten, partially covered ones OR-merged (their target bits must be 0). */
 int zfp_b200_bitcopy(void* d_dst_words, uint64 dst_bit, const void* d_src_words, uint64 src_bit, uint64 nbits,
                      void* cuda_stream);
+
+/* Placement of slab `rank` when the slab lengths are still on the device: d_lengths[r] = bits of slab r
+ * (all-gathered on cuda_stream).  The slab stream at bit 0 of d_src_words goes to
+ * start_bit + d_lengths[0] + ... + d_lengths[rank-1] of d_dst_words (same merge rules as
+ * zfp_b200_bitcopy); that position is also stored to *d_base_out when given.  d_dst_words == NULL only
+ * computes the position. */
+int zfp_b200_bitcopy_ranked(void* d_dst_words, uint64 start_bit, const uint64* d_lengths, uint rank,
+                            const void* d_src_words, uint64* d_base_out, void* cuda_stream);
 
 /* 1 if the parameters make every block the same size (minbits == maxbits) */
 int zfp_b200_is_fixed_rate(const zfp_b200_desc* desc);
@@ -106,6 +135,23 @@ size_t zfp_b200_blocks(const zfp_b200_desc* desc);
 /* capacity in bytes a caller must provide for d_words (zfp_stream_maximum_size formula,
  * src/zfp.c:711-742, plus the words covering start_bit) */
 size_t zfp_b200_capacity(const zfp_b200_desc* desc, uint64 start_bit);
+
+/* ---- (2b) several GPUs, one process ------------------------------------------------------------------
+ * Slab i of the array (block-aligned along the slowest dimension, desc[i] = its extents + the common
+ * parameters) lives on device devices[i].  zfp_b200_multi_compress encodes all slabs concurrently, each at
+ * bit 0 of d_words[i] on its own device and stream, exchanges the slab bit lengths with ncclAllGather
+ * enqueued on those streams and derives each slab's base bit in the global stream on the device; the host
+ * synchronises once, at the end, to read the lengths and bases back (either array may be NULL).  Fixed-rate
+ * slabs need no exchange but go through the same call.  NCCL (ncclCommInitAll) is loaded at run time. */
+typedef struct zfp_b200_multi zfp_b200_multi;
+zfp_b200_multi* zfp_b200_multi_create(int ndev, const int* devices);
+void zfp_b200_multi_destroy(zfp_b200_multi* m);
+int zfp_b200_multi_devices(const zfp_b200_multi* m);
+void* zfp_b200_multi_stream(const zfp_b200_multi* m, int i); /* the cudaStream_t used on device i */
+int zfp_b200_multi_compress(zfp_b200_multi* m, const zfp_b200_desc* descs, const void* const* d_slabs,
+                            void* const* d_words, zfp_b200_index* const* indexes, uint64* slab_bits, uint64* slab_base);
+int zfp_b200_multi_decompress(zfp_b200_multi* m, const zfp_b200_desc* descs, void* const* d_slabs,
+                              const void* const* d_words, zfp_b200_index* const* indexes);
 
 /* ---- (3) block-offset index -------------------------------------------------------------------- */
 zfp_b200_index* zfp_b200_index_create(void);

@@ -29,6 +29,8 @@ ZFP_MAX_BITS = 16658
 
 
 REF_CUDA_SO = os.path.join(HERE, "_ref", "libzfp_ref_cuda.so")
+REF_CUDA_ALL_SO = os.path.join(HERE, "_ref", "libzfp_ref_cuda_all.so")    # reference + integration/zfp_cuda_dispatch.patch on our backend
+REF_CUDA_ORIG_SO = os.path.join(HERE, "_ref", "libzfp_ref_cudaorig.so")   # reference with ITS OWN src/cuda_zfp (the backend replaced)
 
 
 def build(ref=True):
@@ -36,7 +38,7 @@ def build(ref=True):
     have_ref = ref and os.path.isdir(os.environ.get("ZFP_REFERENCE", "/root/reference"))
     targets = ["port"] + (["ref"] if have_ref else [])
     if have_ref and os.path.exists(os.path.join(HERE, "..", "zfp_b200", "lib", "libzfp_b200.so")):
-        targets += ["ref_cuda", "ref_cli"]
+        targets += ["ref_cuda", "ref_cli", "ref_cuda_all", "ref_cudaorig", "b200_cli"]
     subprocess.check_call(["make", "-s", "-C", HERE] + targets)
 
 

@@ -322,11 +322,11 @@ def test_random_access_box_decode(zb):
                                  (np.float64, (9, 12, 8, 10), (4, 0, 3, 2), (9, 5, 8, 7))):
         a = analytic_field(shape, dtype)
         x = torch.from_numpy(a).cuda()
-        for mode in ({"rate": 6}, {"precision": 24}):
+        for mode in ({"rate": 6}, {"rate": 8}, {"precision": 24}, {"accuracy": 1e-4} if np.dtype(dtype).kind == "f" else {"rate": 16}):
             c = zb.compress(x, **mode)
             full = zb.decompress(c)
             out = torch.full_like(full, 55)
-            zb.decompress_box(c, lo, hi, out)
+            zb.decompress_box(c, lo, hi, out)  # one launch over the block list (zfp_b200_decode_box)
             inside = torch.ones(shape, dtype=torch.bool, device="cuda")
             for ax, (l, h) in enumerate(zip(lo, hi)):
                 coord = torch.arange(shape[ax], device="cuda")
@@ -472,3 +472,105 @@ def test_two_host_threads_two_zfp_streams_one_gpu(zb, port):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def _ref_cuda_roundtrip(R, a, mode):
+    """zfp_compress + zfp_decompress of the reference library under zfp_exec_cuda on host arrays."""
+    cuda = R.compress(a, policy=2, **mode)
+    out = np.empty_like(a)
+    n = list(reversed(a.shape)) + [0] * (4 - a.ndim)
+    L = R.L
+    f, dims = R._field(out.ctypes.data, a.dtype, n, None)
+    words = np.concatenate([cuda, np.zeros(4, dtype=np.uint64)])
+    bs = L.stream_open(words.ctypes.data, words.nbytes)
+    z = L.zfp_stream_open(bs)
+    R._set_mode(z, mode, a.dtype, dims)
+    assert L.zfp_stream_set_execution(z, 2)
+    used = L.zfp_decompress(z, f)
+    L.zfp_field_free(f); L.zfp_stream_close(z); L.stream_close(bs)
+    return cuda, out, used
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_patched_reference_dispatch_all_modes_all_dims(dtype):
+    """North-star subsystem (1), executed: the reference library with integration/zfp_cuda_dispatch.patch
+    applied (fixed-rate gate of src/template/cuda{,de}compress.c lifted, 4-D rows of the function tables in
+    src/zfp.c:1085,1089,1145,1149 filled) on our backend.  Through the reference's OWN zfp_compress /
+    zfp_decompress with zfp_exec_cuda, all four modes + expert, 1-4 D, every scalar type give the streams
+    and arrays of its serial policy."""
+    from oracle.oracle import REF_CUDA_ALL_SO, Reference
+    if not os.path.exists(REF_CUDA_ALL_SO):
+        pytest.skip("oracle/_ref/libzfp_ref_cuda_all.so not built (make -C oracle ref_cuda_all)")
+    R = Reference(REF_CUDA_ALL_SO)
+    fp = np.dtype(dtype).kind == "f"
+    modes = [{"rate": 8}, {"rate": 11.5}, {"precision": 17}, {"reversible": True}, {"expert": (30, 900, 40, -40)}]
+    if fp:
+        modes.append({"accuracy": 1e-3})
+    bad = []
+    for shape in ((131,), (37, 42), (18, 21, 25), (6, 9, 7, 10)):
+        for kind in ("smooth", "noise"):
+            a = make_field(shape, dtype, seed=41 + len(shape), kind=kind)
+            for mode in modes:
+                serial = R.compress(a, policy=0, **mode)
+                cuda, out, used = _ref_cuda_roundtrip(R, a, mode)
+                ok = cuda.tobytes() == serial.tobytes() and used == serial.nbytes and \
+                    out.tobytes() == R.decompress(serial, a.shape, a.dtype, **mode).tobytes()
+                if not ok:
+                    bad.append((shape, kind, mode, cuda.nbytes, serial.nbytes, used))
+    assert not bad, bad[:6]
+
+
+def test_patched_reference_cli_variable_rate_reversible_and_4d(tmp_path):
+    """The reference's command-line tool (utils/zfp.c, unmodified) on the patched library: `-x cuda` with
+    -a (fixed accuracy, with a header), -R (reversible) and a 4-D array writes the files `-x serial` writes
+    and decompresses them to the same bytes."""
+    import subprocess
+    from oracle.oracle import HERE as ORACLE_DIR
+    cpu, gpu = os.path.join(ORACLE_DIR, "_ref", "zfp_ref"), os.path.join(ORACLE_DIR, "_ref", "zfp_ref_cuda_all")
+    if not (os.path.exists(cpu) and os.path.exists(gpu)):
+        pytest.skip("oracle/_ref/zfp_ref[_cuda_all] not built")
+    cases = [("acc", (96, 100, 104), ["-d", "-3", "104", "100", "96", "-a", "1e-6", "-h"]),
+             ("rev", (64, 72, 80), ["-d", "-3", "80", "72", "64", "-R", "-h"]),
+             ("prec4d", (12, 16, 20, 24), ["-d", "-4", "24", "20", "16", "12", "-p", "24"]),
+             ("rate4d", (12, 16, 20, 24), ["-d", "-4", "24", "20", "16", "12", "-r", "12", "-h"])]
+    for name, shape, args in cases:
+        a = analytic_field(shape, np.float64)
+        raw = tmp_path / (name + ".raw")
+        a.tofile(raw)
+        got = {}
+        for who, exe, policy in (("cpu", cpu, "serial"), ("gpu", gpu, "cuda")):
+            z, o = tmp_path / ("%s_%s.zfp" % (name, who)), tmp_path / ("%s_%s.out" % (name, who))
+            r = subprocess.run([exe] + args + ["-x", policy, "-i", str(raw), "-z", str(z), "-o", str(o)],
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, (name, who, r.stderr)
+            got[who] = (z.read_bytes(), o.read_bytes())
+        assert got["gpu"][0] == got["cpu"][0], "%s: compressed files differ" % name
+        assert got["gpu"][1] == got["cpu"][1], "%s: decompressed files differ" % name
+
+
+def test_reference_cli_on_libzfp_b200_alone(tmp_path):
+    """utils/zfp.c (unmodified) linked against libzfp_b200.so and nothing else: `-x cuda` writes the stock
+    CPU tool's files in fixed-rate and fixed-accuracy mode; `-x serial` / `-x omp`, which this library
+    leaves to the reference, fail cleanly instead of producing anything."""
+    import subprocess
+    from oracle.oracle import HERE as ORACLE_DIR
+    cpu, ours = os.path.join(ORACLE_DIR, "_ref", "zfp_ref"), os.path.join(ORACLE_DIR, "_ref", "zfp_b200_cli")
+    if not (os.path.exists(cpu) and os.path.exists(ours)):
+        pytest.skip("oracle/_ref/zfp_ref / zfp_b200_cli not built")
+    a = analytic_field((72, 80, 88), np.float64)
+    raw = tmp_path / "f.raw"
+    a.tofile(raw)
+    dims = ["-d", "-3", "88", "80", "72"]
+    for name, args in (("rate", ["-r", "10", "-h"]), ("acc", ["-a", "1e-5", "-h"])):
+        files = {}
+        for who, exe, policy in (("cpu", cpu, "serial"), ("ours", ours, "cuda")):
+            z, o = tmp_path / ("%s_%s.zfp" % (name, who)), tmp_path / ("%s_%s.out" % (name, who))
+            r = subprocess.run([exe] + dims + args + ["-x", policy, "-i", str(raw), "-z", str(z), "-o", str(o)],
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, (name, who, r.stderr)
+            files[who] = (z.read_bytes(), o.read_bytes())
+        assert files["ours"] == files["cpu"], name
+    for policy in ("serial", "omp"):
+        r = subprocess.run([ours] + dims + ["-r", "8", "-x", policy, "-i", str(raw), "-z", str(tmp_path / "no.zfp")],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode != 0 and not (tmp_path / "no.zfp").exists() or (tmp_path / "no.zfp").stat().st_size == 0, policy

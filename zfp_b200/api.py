@@ -77,6 +77,7 @@ _PROTOTYPES = {
     "zfp_stream_set_params": (C.c_int, [_vp, C.c_uint, C.c_uint, C.c_uint, C.c_int]),
     "zfp_stream_execution": (C.c_int, [_vp]), "zfp_stream_set_execution": (C.c_int, [_vp, C.c_int]),
     "zfp_stream_omp_threads": (C.c_uint, [_vp]), "zfp_stream_omp_chunk_size": (C.c_uint, [_vp]),
+    "zfp_stream_set_omp_threads": (C.c_int, [_vp, C.c_uint]), "zfp_stream_set_omp_chunk_size": (C.c_int, [_vp, C.c_uint]),
     "zfp_compress": (_sz, [_vp, _vp]), "zfp_decompress": (_sz, [_vp, _vp]),
     "zfp_write_header": (_sz, [_vp, _vp, C.c_uint]), "zfp_read_header": (_sz, [_vp, _vp, C.c_uint]),
     # backend C ABI
@@ -84,9 +85,18 @@ _PROTOTYPES = {
     "zfp_b200_compress_stream": (_sz, [_vp, _vp]), "zfp_b200_decompress_stream": (_sz, [_vp, _vp]),
     "zfp_stream_cuda_params": (C.POINTER(CudaParams), [_vp]),
     "zfp_b200_encode": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp]),
+    "zfp_b200_encode_async": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
     "zfp_b200_decode": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(C.c_uint64), _vp, _vp]),
+    "zfp_b200_decode_async": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
+    "zfp_b200_decode_box": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.POINTER(_sz), C.POINTER(_sz), _vp, _vp]),
     "zfp_b200_decode_blocks": (C.c_int, [C.POINTER(Desc), _vp, _vp, C.c_uint64, C.c_uint64, C.c_uint64, _vp, _vp]),
     "zfp_b200_bitcopy": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64, _vp]),
+    "zfp_b200_bitcopy_ranked": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint, _vp, _vp, _vp]),
+    "zfp_b200_multi_create": (_vp, [C.c_int, C.POINTER(C.c_int)]), "zfp_b200_multi_destroy": (None, [_vp]),
+    "zfp_b200_multi_devices": (C.c_int, [_vp]), "zfp_b200_multi_stream": (_vp, [_vp, C.c_int]),
+    "zfp_b200_multi_compress": (C.c_int, [_vp, C.POINTER(Desc), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "zfp_b200_multi_decompress": (C.c_int, [_vp, C.POINTER(Desc), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "zfp_b200_is_fixed_rate": (C.c_int, [C.POINTER(Desc)]), "zfp_b200_blocks": (_sz, [C.POINTER(Desc)]),
     "zfp_b200_capacity": (_sz, [C.POINTER(Desc), C.c_uint64]),
     "zfp_b200_index_create": (_vp, []), "zfp_b200_index_destroy": (None, [_vp]), "zfp_b200_index_bits": (C.c_uint64, [_vp]),
@@ -384,9 +394,27 @@ def decompress_box(c, lo, hi, out):
     """Random access by coordinates: decode every block that intersects the box lo <= index < hi
     (one (lo, hi) pair per array dimension, slowest first, like the tensor's shape) into `out`.
     Blocks are decoded whole, so values of `out` up to 3 positions outside the box along each
-    dimension are written too.  One block-range launch per row of blocks along the fastest dimension."""
-    for b0, b1 in box_block_ranges(tuple(out.shape), lo, hi):
-        decompress_blocks(c, b0, b1, out)
+    dimension are written too.  ONE kernel launch over the list of blocks (zfp_b200_decode_box)."""
+    L = load_library()
+    dims = out.dim()
+    if len(lo) != dims or len(hi) != dims:
+        raise ValueError("lo / hi need one entry per dimension")
+    minbits, maxbits, maxprec, minexp = mode_params(c.mode, str(out.dtype).split(".")[-1], dims)
+    d = Desc()
+    d.type, d.dims = _tensor_type(out), dims
+    for i, (n, st) in enumerate(zip(reversed(out.shape), reversed(out.stride()))):
+        d.n[i], d.s[i] = n, st
+    d.minbits, d.maxbits, d.maxprec, d.minexp = minbits, maxbits, maxprec, minexp
+    blo, bhi = (_sz * 4)(), (_sz * 4)()
+    for i, (l, h) in enumerate(zip(reversed(lo), reversed(hi))):
+        blo[i], bhi[i] = max(0, int(l)), max(0, int(h))
+    index = None
+    if minbits != maxbits:
+        p = L.zfp_stream_cuda_params(c.stream.z)
+        index = p.contents.index if p else None
+    rc = L.zfp_b200_decode_box(C.byref(d), out.data_ptr(), c.words.data_ptr(), c.start_bit, blo, bhi, index, None)
+    if rc:
+        raise RuntimeError("zfp_b200_decode_box failed: %s" % last_error())
     return out
 
 

@@ -14,6 +14,7 @@
 #include <string>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include "../../include/zfp_b200_backend.h"
 #include "bitstream_impl.h"
@@ -249,6 +250,11 @@ static bool make_geom(const zfp_b200_desc* d, const void* data, Geom* g)
   for (uint32_t i = 1; i < d->dims; i++)
     vec = vec && (g->s[i] % 4) == 0;
   g->vec_rows = vec ? 1 : 0;
+  g->box = 0;
+  for (int i = 0; i < 4; i++) {
+    g->bl[i] = 0;
+    g->be[i] = 1;
+  }
   return true;
 }
 
@@ -373,8 +379,29 @@ __global__ void set_cursor(uint64_t* cursor, uint64_t v) { cursor[0] = v; cursor
 // ------------------------------------------------------------------------------------------------
 // raw entry points
 // ------------------------------------------------------------------------------------------------
+__global__ void store_u64(uint64_t* dst, uint64_t v) { *dst = v; }
+__global__ void copy_u64(uint64_t* dst, const uint64_t* src) { *dst = *src; }
+
+// d_end_bit != nullptr: the end position is left in DEVICE memory and nothing synchronises the stream
+// (variable rate: the host never learns the size; the index's total_bits stays 0)
+static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words, uint64 start_bit,
+                       uint64* end_bit, uint64* d_end_bit, zfp_b200_index* index, void* cuda_stream);
+
 extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void* d_words, uint64 start_bit,
                                uint64* end_bit, zfp_b200_index* index, void* cuda_stream)
+{
+  return encode_impl(d, d_data, d_words, start_bit, end_bit, nullptr, index, cuda_stream);
+}
+
+extern "C" int zfp_b200_encode_async(const zfp_b200_desc* d, const void* d_data, void* d_words, uint64 start_bit,
+                                     uint64* d_end_bit, zfp_b200_index* index, void* cuda_stream)
+{
+  if (!d_end_bit) return ZFP_B200_EINVAL;
+  return encode_impl(d, d_data, d_words, start_bit, nullptr, d_end_bit, index, cuda_stream);
+}
+
+static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words, uint64 start_bit,
+                       uint64* end_bit, uint64* d_end_bit, zfp_b200_index* index, void* cuda_stream)
 {
   Geom g;
   if (!make_geom(d, d_data, &g) || !d_data || !d_words) {
@@ -414,6 +441,10 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
     }
     if (rc) return rc;
     if (end_bit) *end_bit = end;
+    if (d_end_bit) {
+      store_u64<<<1, 1, 0, st>>>(d_end_bit, end);
+      LAUNCHED();
+    }
     return ZFP_B200_OK;
   }
 
@@ -453,26 +484,40 @@ extern "C" int zfp_b200_encode(const zfp_b200_desc* d, const void* d_data, void*
     compact_blocks<<<(unsigned)((cn * kCompactLanes + 255) / 256), 256, 0, st>>>(slots, slot_words, lengths + b0, offsets, cn, d_words);
     LAUNCHED();
   }
+  if (index) {
+    index->keyed = true;
+    index->key_desc = *d;
+    index->key_start = start_bit;
+    index->total_bits = 0;
+  }
+  if (d_end_bit) {  // stream-ordered: the size stays on the device
+    copy_u64<<<1, 1, 0, st>>>(d_end_bit, cursor + 1);
+    LAUNCHED();
+    return ZFP_B200_OK;
+  }
   uint64_t h_cursor[2];
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (end_bit) *end_bit = h_cursor[1];
-  if (index) {
-    index->total_bits = h_cursor[1] - start_bit;
-    index->keyed = true;
-    index->key_desc = *d;
-    index->key_start = start_bit;
-  }
+  if (index) index->total_bits = h_cursor[1] - start_bit;
   return ZFP_B200_OK;
 }
 
 static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit, uint64* end_bit,
-                        const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole);
+                        const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole,
+                        uint32_t* d_status = nullptr, const size_t* box_lo = nullptr, const size_t* box_hi = nullptr);
 
 extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
                                uint64* end_bit, const zfp_b200_index* index, void* cuda_stream)
 {
   return decode_range(d, d_data, d_words, start_bit, end_bit, index, cuda_stream, 0, 0, true);
+}
+
+extern "C" int zfp_b200_decode_async(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
+                                     const zfp_b200_index* index, uint32_t* d_status, void* cuda_stream)
+{
+  if (!d_status) return ZFP_B200_EINVAL;
+  return decode_range(d, d_data, d_words, start_bit, nullptr, index, cuda_stream, 0, 0, true, d_status);
 }
 
 extern "C" int zfp_b200_decode_blocks(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
@@ -481,8 +526,16 @@ extern "C" int zfp_b200_decode_blocks(const zfp_b200_desc* d, void* d_data, cons
   return decode_range(d, d_data, d_words, start_bit, nullptr, index, cuda_stream, block0, block1, false);
 }
 
+extern "C" int zfp_b200_decode_box(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
+                                   const size_t* lo, const size_t* hi, const zfp_b200_index* index, void* cuda_stream)
+{
+  if (!lo || !hi) return ZFP_B200_EINVAL;
+  return decode_range(d, d_data, d_words, start_bit, nullptr, index, cuda_stream, 0, 0, false, nullptr, lo, hi);
+}
+
 static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit, uint64* end_bit,
-                        const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole)
+                        const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole,
+                        uint32_t* d_status, const size_t* box_lo, const size_t* box_hi)
 {
   Geom g;
   if (!make_geom(d, d_data, &g) || !d_data || !d_words) {
@@ -500,6 +553,25 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
   if (whole) {
     block0 = 0;
     block1 = g.nblocks;
+  }
+  else if (box_lo) {
+    // the blocks that intersect lo <= index < hi (x first, like desc->n): one launch over their list
+    uint64_t count = 1;
+    for (uint32_t i = 0; i < 4; i++) {
+      uint64_t l = 0, h = 1;
+      if (i < d->dims) {
+        const uint64_t hi_i = box_hi[i] < g.n[i] ? box_hi[i] : g.n[i];
+        if (box_lo[i] >= hi_i) return ZFP_B200_OK;  // empty box
+        l = box_lo[i] / 4;
+        h = (hi_i + 3) / 4;
+      }
+      g.bl[i] = (uint32_t)l;
+      g.be[i] = (uint32_t)(h - l);
+      count *= h - l;
+    }
+    g.box = 1;
+    block0 = 0;
+    block1 = count;
   }
   else if (block0 > block1 || block1 > g.nblocks) {
     g_error = "zfp_b200_decode_blocks: block range outside the field";
@@ -519,6 +591,10 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
   // since, or the buffer may have been refilled.  A stale index costs one wasted decode, never wrong data.
   const uint16_t* lengths;
   const bool use_index = index_matches(index, d, g, start_bit);
+  if (d_status && !use_index) {
+    g_error = "zfp_b200_decode_async: variable-rate parameters need the block index of this stream";
+    return ZFP_B200_ENOINDEX;
+  }
   if (use_index)
     lengths = index->d_lengths;
   else {
@@ -546,8 +622,10 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
   rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st);
   if (rc) return rc;
   rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st, block0, block1,
-                  reinterpret_cast<uint32_t*>(cursor + 2));
+                  d_status ? d_status : reinterpret_cast<uint32_t*>(cursor + 2));
   if (rc) return rc;
+  if (d_status)  // stream-ordered: the caller looks at *d_status (0 = every block parsed to its indexed length) when it likes
+    return ZFP_B200_OK;
   uint64_t h_cursor[3];
   CU(cudaMemcpyAsync(h_cursor, cursor, sizeof(h_cursor), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -576,6 +654,240 @@ extern "C" int zfp_b200_bitcopy(void* d_dst_words, uint64 dst_bit, const void* d
                                                                            static_cast<const uint64_t*>(d_src_words), src_bit, nbits);
   LAUNCHED();
   return ZFP_B200_OK;
+}
+
+// Slab placement with the offsets still on the device: d_end_bits[r] = end bit of rank r's slab stream
+// encoded at bit 0 of its own buffer (= its length), as all-gathered on this stream; slab `rank` goes to
+// start_bit + sum of the lengths of the lower ranks.  No host round trip between the encode, the
+// exchange and the placement.
+__global__ void __launch_bounds__(256)
+bitcopy_ranked_kernel(uint64_t* __restrict__ dst, uint64_t start_bit, const uint64_t* __restrict__ lens, uint32_t rank,
+                      const uint64_t* __restrict__ src, uint64_t* __restrict__ d_base_out)
+{
+  uint64_t dst_bit = start_bit;
+  for (uint32_t r = 0; r < rank; r++)
+    dst_bit += lens[r];
+  const uint64_t nbits = lens[rank];
+  if (d_base_out && blockIdx.x == 0 && threadIdx.x == 0)
+    *d_base_out = dst_bit;
+  if (!dst)
+    return;
+  const uint64_t w0 = dst_bit >> 6, w1 = (dst_bit + nbits + 63) >> 6;
+  for (uint64_t w = w0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < w1; w += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t lo = w * 64 > dst_bit ? w * 64 : dst_bit;
+    const uint64_t hi = (w + 1) * 64 < dst_bit + nbits ? (w + 1) * 64 : dst_bit + nbits;
+    const uint32_t len = (uint32_t)(hi - lo);
+    const uint64_t sb = lo - dst_bit;
+    const uint32_t sh = (uint32_t)(sb & 63);
+    uint64_t v = src[sb >> 6] >> sh;
+    if (sh && sh + len > 64)
+      v |= src[(sb >> 6) + 1] << (64 - sh);
+    v &= len >= 64 ? ~0ull : ((1ull << len) - 1);
+    v <<= (uint32_t)(lo & 63);
+    if (len == 64)
+      dst[w] = v;
+    else
+      atomicOr(reinterpret_cast<unsigned long long*>(dst + w), (unsigned long long)v);
+  }
+}
+
+extern "C" int zfp_b200_bitcopy_ranked(void* d_dst_words, uint64 start_bit, const uint64* d_lengths, uint rank,
+                                       const void* d_src_words, uint64* d_base_out, void* cuda_stream)
+{
+  if (!d_lengths || (d_dst_words && !d_src_words)) return ZFP_B200_EINVAL;
+  const unsigned ctas = d_dst_words ? (unsigned)sm_count() * 8 : 1;
+  bitcopy_ranked_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(cuda_stream)>>>(
+      static_cast<uint64_t*>(d_dst_words), start_bit, d_lengths, rank, static_cast<const uint64_t*>(d_src_words), d_base_out);
+  LAUNCHED();
+  return ZFP_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Several GPUs driven by ONE process (SURVEY section 8e "process model"): slab i of the array lives on
+// device i; the slabs are encoded concurrently, each on its device's stream, and the only exchange of
+// the variable-rate path - one 64-bit slab length per device - is an ncclAllGather enqueued on those
+// same streams, followed by the device-side prefix that gives every slab its place in the global
+// stream.  Nothing returns to the host between the encode and the placement; one synchronisation at the
+// end delivers the lengths.  NCCL is resolved at run time (dlopen of libnccl.so.2, the library torch
+// ships or the system one), so libzfp_b200.so itself has no NCCL dependency.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef void* nccl_comm_t;
+struct NcclApi {
+  int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(nccl_comm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclUint64 = 5;  // ncclUint64 (nccl.h ncclDataType_t)
+
+NcclApi* nccl_api()
+{
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+    api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+    api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    api.ok = api.CommInitAll && api.CommDestroy && api.AllGather && api.GroupStart && api.GroupEnd;
+  });
+  return &api;
+}
+
+}  // namespace
+
+struct zfp_b200_multi {
+  int ndev = 0;
+  int dev[16];
+  nccl_comm_t comm[16];
+  cudaStream_t stream[16];
+  uint64_t* d_len[16];    // this device's slab length (bits)
+  uint64_t* d_all[16];    // all slab lengths, gathered
+  uint64_t* d_base[16];   // this device's slab base in the global stream
+  uint64_t* h_pinned = nullptr;  // [2 * ndev]: lengths, bases
+};
+
+extern "C" void zfp_b200_multi_destroy(zfp_b200_multi* m)
+{
+  if (!m) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  NcclApi* nc = nccl_api();
+  for (int i = 0; i < m->ndev; i++) {
+    cudaSetDevice(m->dev[i]);
+    if (m->stream[i]) cudaStreamSynchronize(m->stream[i]);
+    if (m->comm[i] && nc->ok) nc->CommDestroy(m->comm[i]);
+    if (m->d_len[i]) cudaFree(m->d_len[i]);
+    if (m->stream[i]) cudaStreamDestroy(m->stream[i]);
+  }
+  if (m->h_pinned) cudaFreeHost(m->h_pinned);
+  cudaSetDevice(cur);
+  delete m;
+}
+
+extern "C" zfp_b200_multi* zfp_b200_multi_create(int ndev, const int* devices)
+{
+  NcclApi* nc = nccl_api();
+  if (ndev < 1 || ndev > 16 || !devices) {
+    g_error = "zfp_b200_multi_create: 1..16 devices";
+    return nullptr;
+  }
+  if (!nc->ok) {
+    g_error = "zfp_b200_multi_create: libnccl.so.2 not found (dlopen)";
+    return nullptr;
+  }
+  zfp_b200_multi* m = new (std::nothrow) zfp_b200_multi();
+  if (!m) return nullptr;
+  m->ndev = ndev;
+  for (int i = 0; i < 16; i++) {
+    m->dev[i] = i < ndev ? devices[i] : -1;
+    m->comm[i] = nullptr;
+    m->stream[i] = nullptr;
+    m->d_len[i] = m->d_all[i] = m->d_base[i] = nullptr;
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  bool ok = true;
+  const int rc = nc->CommInitAll(m->comm, ndev, m->dev);
+  if (rc != 0) {
+    g_error = std::string("ncclCommInitAll: ") + (nc->GetErrorString ? nc->GetErrorString(rc) : "failed");
+    ok = false;
+  }
+  for (int i = 0; i < ndev && ok; i++) {
+    ok = cuda_ok(cudaSetDevice(m->dev[i]), "cudaSetDevice") &&
+         cuda_ok(cudaStreamCreateWithFlags(&m->stream[i], cudaStreamNonBlocking), "cudaStreamCreate") &&
+         cuda_ok(cudaMalloc(&m->d_len[i], (size_t)(ndev + 2) * 8), "cudaMalloc(multi)");
+    if (ok) {
+      m->d_all[i] = m->d_len[i] + 1;
+      m->d_base[i] = m->d_len[i] + 1 + ndev;
+    }
+  }
+  ok = ok && cuda_ok(cudaMallocHost(&m->h_pinned, (size_t)ndev * 16), "cudaMallocHost(multi)");
+  cudaSetDevice(cur);
+  if (!ok) {
+    zfp_b200_multi_destroy(m);
+    return nullptr;
+  }
+  return m;
+}
+
+extern "C" int zfp_b200_multi_devices(const zfp_b200_multi* m) { return m ? m->ndev : 0; }
+extern "C" void* zfp_b200_multi_stream(const zfp_b200_multi* m, int i) { return m && i >= 0 && i < m->ndev ? m->stream[i] : nullptr; }
+
+extern "C" int zfp_b200_multi_compress(zfp_b200_multi* m, const zfp_b200_desc* descs, const void* const* d_slabs,
+                                       void* const* d_words, zfp_b200_index* const* indexes, uint64* slab_bits, uint64* slab_base)
+{
+  if (!m || !descs || !d_slabs || !d_words) return ZFP_B200_EINVAL;
+  NcclApi* nc = nccl_api();
+  int cur = 0, rc = ZFP_B200_OK;
+  cudaGetDevice(&cur);
+  // 1. every slab encoded at bit 0 of its own buffer, length left in device memory
+  for (int i = 0; i < m->ndev && rc == ZFP_B200_OK; i++) {
+    if (!cuda_ok(cudaSetDevice(m->dev[i]), "cudaSetDevice")) rc = ZFP_B200_ECUDA;
+    else rc = zfp_b200_encode_async(&descs[i], d_slabs[i], d_words[i], 0, m->d_len[i], indexes ? indexes[i] : nullptr, m->stream[i]);
+  }
+  // 2. the exchange, on the same streams
+  if (rc == ZFP_B200_OK) {
+    int e = nc->GroupStart();
+    for (int i = 0; i < m->ndev && e == 0; i++)
+      e = nc->AllGather(m->d_len[i], m->d_all[i], 1, kNcclUint64, m->comm[i], m->stream[i]);
+    const int e2 = nc->GroupEnd();
+    if (e != 0 || e2 != 0) {
+      g_error = std::string("ncclAllGather: ") + (nc->GetErrorString ? nc->GetErrorString(e ? e : e2) : "failed");
+      rc = ZFP_B200_ECUDA;
+    }
+  }
+  // 3. device-side prefix: where each slab starts in the global stream; results to the host in one go
+  for (int i = 0; i < m->ndev && rc == ZFP_B200_OK; i++) {
+    if (!cuda_ok(cudaSetDevice(m->dev[i]), "cudaSetDevice")) { rc = ZFP_B200_ECUDA; break; }
+    rc = zfp_b200_bitcopy_ranked(nullptr, 0, m->d_all[i], (uint)i, nullptr, m->d_base[i], m->stream[i]);
+    if (rc == ZFP_B200_OK && (slab_bits || slab_base)) {
+      if (!cuda_ok(cudaMemcpyAsync(m->h_pinned + i, m->d_len[i], 8, cudaMemcpyDeviceToHost, m->stream[i]), "D2H length") ||
+          !cuda_ok(cudaMemcpyAsync(m->h_pinned + m->ndev + i, m->d_base[i], 8, cudaMemcpyDeviceToHost, m->stream[i]), "D2H base"))
+        rc = ZFP_B200_ECUDA;
+    }
+  }
+  for (int i = 0; i < m->ndev; i++) {
+    cudaSetDevice(m->dev[i]);
+    if (!cuda_ok(cudaStreamSynchronize(m->stream[i]), "sync") && rc == ZFP_B200_OK) rc = ZFP_B200_ECUDA;
+  }
+  cudaSetDevice(cur);
+  if (rc == ZFP_B200_OK)
+    for (int i = 0; i < m->ndev; i++) {
+      if (slab_bits) slab_bits[i] = m->h_pinned[i];
+      if (slab_base) slab_base[i] = m->h_pinned[m->ndev + i];
+    }
+  return rc;
+}
+
+extern "C" int zfp_b200_multi_decompress(zfp_b200_multi* m, const zfp_b200_desc* descs, void* const* d_slabs,
+                                         const void* const* d_words, zfp_b200_index* const* indexes)
+{
+  if (!m || !descs || !d_slabs || !d_words) return ZFP_B200_EINVAL;
+  int cur = 0, rc = ZFP_B200_OK;
+  cudaGetDevice(&cur);
+  // fixed-rate slabs are enqueued on all devices before anything waits; variable-rate ones synchronise their
+  // own stream at the end of each call (index check), so they overlap only across the launches already queued
+  for (int i = 0; i < m->ndev && rc == ZFP_B200_OK; i++) {
+    if (!cuda_ok(cudaSetDevice(m->dev[i]), "cudaSetDevice")) rc = ZFP_B200_ECUDA;
+    else rc = zfp_b200_decode(&descs[i], d_slabs[i], d_words[i], 0, nullptr, indexes ? indexes[i] : nullptr, m->stream[i]);
+  }
+  for (int i = 0; i < m->ndev; i++) {
+    cudaSetDevice(m->dev[i]);
+    if (!cuda_ok(cudaStreamSynchronize(m->stream[i]), "sync") && rc == ZFP_B200_OK) rc = ZFP_B200_ECUDA;
+  }
+  cudaSetDevice(cur);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -190,10 +190,10 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
   constexpr int N = 1 << (2 * DIMS);
   if constexpr (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) {
     static const bool q4 = getenv("ZFP_B200_Q4") != nullptr;
-    if (q4 && (kQ4Threads / 32) * q4_warp_bytes(a.prm.maxbits >> 5) <= 200 * 1024)
+    if (q4 && !a.g.box && (kQ4Threads / 32) * q4_warp_bytes(a.prm.maxbits >> 5) <= 200 * 1024)
       return run_decode_q4<TYPE>(a);
     static const bool ws = getenv("ZFP_B200_WS") != nullptr && ws_cta_bytes(4096 >> 5) > 0;
-    if (ws && ws_cta_bytes(a.prm.maxbits >> 5) <= 110 * 1024)
+    if (ws && !a.g.box && ws_cta_bytes(a.prm.maxbits >> 5) <= 110 * 1024)
       return run_decode_ws<TYPE>(a);
   }
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;

@@ -329,7 +329,8 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
 
   const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;  // no early exit (warp-wide votes in decode_block)
-  const uint64_t b = valid ? b_raw : block1 - 1;
+  const uint64_t b_list = valid ? b_raw : block1 - 1;
+  const uint64_t b = g.box ? box_block(g, b_list) : b_list;
   const uint32_t* src32 = reinterpret_cast<const uint32_t*>(in + (start_bit >> 6)) + b * (uint64_t)words;
   const uint64_t* src = reinterpret_cast<const uint64_t*>(src32);
   if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(src32) & 15) == 0) {
@@ -437,7 +438,8 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
 
   const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
   const bool valid = b_raw < block1;
-  const uint64_t b = valid ? b_raw : block1 - 1;
+  const uint64_t b_list = valid ? b_raw : block1 - 1;
+  const uint64_t b = g.box ? box_block(g, b_list) : b_list;
   const uint64_t off = offsets[b];
   const uint32_t phase = (uint32_t)(off & 31), len = lengths[b];
   ColReader br;
@@ -467,9 +469,10 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   extern __shared__ uint64_t smem_raw[];
   PW* sp = reinterpret_cast<PW*>(smem_raw) + (threadIdx.x >> 5) * (TR::P * 32) + (threadIdx.x & 31);
 
-  const uint64_t b = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (b >= block1)
+  const uint64_t b_list = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (b_list >= block1)
     return;
+  const uint64_t b = g.box ? box_block(g, b_list) : b_list;
   BitReader br;
   br.init(in, OFFS ? offsets[b] : start_bit + b * (uint64_t)prm.maxbits);
   typename TR::Scalar v[N];

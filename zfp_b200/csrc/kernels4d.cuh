@@ -343,8 +343,9 @@ decode4_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params 
   using Int = typename TR::Int;
   using UInt = typename TR::UInt;
   constexpr int P = TR::P;
-  const uint64_t b = block0 + (uint64_t)blockIdx.x * kThreads4 + threadIdx.x;
-  if (b >= block1) return;
+  const uint64_t b_list = block0 + (uint64_t)blockIdx.x * kThreads4 + threadIdx.x;
+  if (b_list >= block1) return;
+  const uint64_t b = g.box ? box_block(g, b_list) : b_list;
 
   Scalar v[256];
   Int q[256];

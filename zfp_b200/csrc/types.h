@@ -16,7 +16,25 @@ struct Geom {
   uint64_t nb[4];   // blocks per dimension
   uint64_t nblocks;
   int vec_rows;     // 1: sx == 1 and every 4-value row starts 16/32-byte aligned
+  // decode of a coordinate box in one launch (zfp_b200_decode_box): when box != 0 the decode kernels walk the
+  // list of blocks that intersect the box - be[0]*be[1]*be[2]*be[3] of them, x fastest - and map list position
+  // i to block number sum_d (bl[d] + i_d) * prod_{e<d} nb[e]
+  int box;
+  uint32_t bl[4], be[4];
 };
+
+// list position inside the box -> block number of the array
+__host__ __device__ inline uint64_t box_block(const Geom& g, uint64_t i)
+{
+  uint64_t b = 0, mul = 1;
+  for (int d = 0; d < 4; d++) {
+    const uint64_t q = i / g.be[d], c = i - q * g.be[d];
+    b += (g.bl[d] + c) * mul;
+    mul *= g.nb[d];
+    i = q;
+  }
+  return b;
+}
 
 struct Params {
   uint32_t minbits, maxbits, maxprec;

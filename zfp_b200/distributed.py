@@ -144,3 +144,81 @@ def gather_stream_cuda(c, nbits, base, total_bits, group=None):
         api.bitcopy(out, bs, part, 0, nb)
     torch.cuda.synchronize()
     return out
+
+
+# --------------------------------------------------------------------------------------------------
+# stream-ordered device path: no host round trip between the encode, the exchange and the placement
+# --------------------------------------------------------------------------------------------------
+class DeviceSlab:
+    """One rank's slab codec with everything the variable-rate exchange needs kept on the device.
+
+    compress() enqueues, on the current CUDA stream: the slab encode (zfp_b200_encode_async: the slab's bit
+    length stays in device memory), the all_gather of the slab lengths (NCCL, same stream order) and the
+    device-side prefix / placement (zfp_b200_bitcopy_ranked).  Nothing is read back; `lengths` and `base`
+    are device tensors the caller may look at whenever it chooses to synchronise."""
+
+    def __init__(self, slab_shape, dtype, mode, rank, world, group=None, device=None):
+        import torch
+        from . import api
+        self.torch, self.api = torch, api
+        self.L = api.load_library()
+        self.rank, self.world, self.group = rank, world, group
+        self.shape, self.dtype, self.mode = tuple(slab_shape), dtype, dict(mode)
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        name = str(dtype).split(".")[-1]
+        mn, mx, mp, me = api.mode_params(self.mode, name, len(self.shape))
+        d = api.Desc()
+        d.type, d.dims = api.ZFP_TYPE[name], len(self.shape)
+        for i, n in enumerate(reversed(self.shape)):
+            d.n[i], d.s[i] = n, 0
+        d.minbits, d.maxbits, d.maxprec, d.minexp = mn, mx, mp, me
+        self.desc = d
+        self.fixed = mn == mx
+        self.words = torch.zeros(self.L.zfp_b200_capacity(api.C.byref(d), 0) // 8 + 2, dtype=torch.int64, device=dev)
+        self.index = None if self.fixed else self.L.zfp_b200_index_create()
+        self.my_bits = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lengths = torch.zeros(world, dtype=torch.int64, device=dev)
+        self.base = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)  # decode-time index check, accumulated over calls
+
+    def close(self):
+        if self.index:
+            self.L.zfp_b200_index_destroy(self.index)
+            self.index = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def compress(self, slab, global_words=None, start_bit=0):
+        """slab: contiguous CUDA tensor of self.shape.  Optionally also places the slab stream in
+        `global_words` (an int64 CUDA tensor, zeroed where slabs will land)."""
+        torch, api = self.torch, self.api
+        import torch.distributed as dist
+        assert slab.is_contiguous() and tuple(slab.shape) == self.shape
+        st = torch.cuda.current_stream().cuda_stream
+        rc = self.L.zfp_b200_encode_async(api.C.byref(self.desc), slab.data_ptr(), self.words.data_ptr(), 0,
+                                          self.my_bits.data_ptr(), self.index, st)
+        if rc:
+            raise RuntimeError("zfp_b200_encode_async failed: %s" % api.last_error())
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.lengths, self.my_bits, group=self.group)  # stream-ordered, no host sync
+        else:
+            self.lengths.copy_(self.my_bits)
+        rc = self.L.zfp_b200_bitcopy_ranked(global_words.data_ptr() if global_words is not None else None, start_bit,
+                                            self.lengths.data_ptr(), self.rank, self.words.data_ptr(), self.base.data_ptr(), st)
+        if rc:
+            raise RuntimeError("zfp_b200_bitcopy_ranked failed: %s" % api.last_error())
+
+    def decompress(self, out):
+        """Decode this rank's slab from its local stream (variable rate: through the block index the encode
+        left), stream ordered: `status` (device) turns non-zero if a block did not parse to its indexed length."""
+        torch, api = self.torch, self.api
+        st = torch.cuda.current_stream().cuda_stream
+        rc = self.L.zfp_b200_decode_async(api.C.byref(self.desc), out.data_ptr(), self.words.data_ptr(), 0, self.index,
+                                          self.status.data_ptr(), st)
+        if rc:
+            raise RuntimeError("zfp_b200_decode_async failed: %s" % api.last_error())
+        return out
