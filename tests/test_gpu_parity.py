@@ -574,3 +574,39 @@ def test_reference_cli_on_libzfp_b200_alone(tmp_path):
         r = subprocess.run([ours] + dims + ["-r", "8", "-x", policy, "-i", str(raw), "-z", str(tmp_path / "no.zfp")],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode != 0 and not (tmp_path / "no.zfp").exists() or (tmp_path / "no.zfp").stat().st_size == 0, policy
+
+
+def test_single_pass_variable_rate_encoder_is_bit_exact():
+    """The single-pass variable-rate encoder (kernels_var1.cuh: decoupled look-back, no slot scratch; opt-in with
+    ZFP_B200_VAR1=1 because it measured slower than the slot path) against the oracle, in a fresh process: smooth
+    and noisy data (blocks that outgrow the shared-memory window are re-encoded into their holes), several tiles,
+    a header before the payload, the probe / hand-over for data with mostly long blocks."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "%s"); sys.path.insert(0, "%s/tests")
+import zfp_b200 as zb
+from oracle.oracle import Port
+from helpers import analytic_field, make_field
+P = Port(); bad = []
+for dtype, shape in ((np.float64, (68, 72, 80)), (np.float32, (40, 44, 52)), (np.int32, (36, 40, 44)), (np.float64, (260, 264, 272))):
+    for kind in ("smooth", "noise"):
+        a = make_field(shape, dtype, seed=7, kind=kind) if shape[0] < 200 else (analytic_field(shape, dtype) if kind == "smooth" else make_field(shape, dtype, seed=8, kind="noise"))
+        x = torch.from_numpy(a).cuda()
+        for mode in ({"precision": 19}, {"accuracy": 1e-4}, {"reversible": True}, {"expert": (64, 3000, 50, -60)}):
+            if np.dtype(dtype).kind != "f" and "accuracy" in mode: continue
+            if shape[0] > 200 and "expert" in mode: continue
+            want = P.compress(a, **mode)
+            c = zb.compress(x, header=False, **mode)
+            ok = c.to_numpy().tobytes() == want.tobytes() and zb.decompress(c).cpu().numpy().tobytes() == P.decompress(want, a.shape, a.dtype, **mode).tobytes()
+            buf = torch.zeros(zb.max_stream_words(x.shape, x.dtype, mode, 77), dtype=torch.int64, device="cuda")
+            c2 = zb.compress(x, out=buf, start_bit=77, **mode)
+            w2 = P.compress_raw(a.reshape(-1), 0, a.dtype, list(reversed(a.shape)) + [0], None, mode, start_bit=77)[0]
+            ok = ok and (c2.to_numpy().tobytes() == w2[:len(c2.to_numpy())].tobytes())
+            if not ok: bad.append((np.dtype(dtype).name, shape, kind, mode))
+print("BAD", bad) if bad else print("VAR1 OK", zb.launch_count())
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, ZFP_B200_VAR1="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "VAR1 OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

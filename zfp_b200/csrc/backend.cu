@@ -382,6 +382,147 @@ __global__ void set_cursor(uint64_t* cursor, uint64_t v) { cursor[0] = v; cursor
 __global__ void store_u64(uint64_t* dst, uint64_t v) { *dst = v; }
 __global__ void copy_u64(uint64_t* dst, const uint64_t* src) { *dst = *src; }
 
+// carry = {end position, last 64 bits of the stream so far}: the payload starts at start_bit, whatever a
+// header left below it in its word is the tail the first tile completes
+__global__ void init_carry(unsigned long long* carry, const uint64_t* words, uint64_t start_bit)
+{
+  const uint32_t r = (uint32_t)(start_bit & 63);
+  carry[0] = start_bit;
+  carry[1] = r ? (words[start_bit >> 6] & ((1ull << r) - 1)) << (64 - r) : 0;
+}
+
+__global__ void finish_async_var1(uint64_t* d_end, const unsigned long long* carry, const unsigned int* count, unsigned int capacity)
+{
+  *d_end = *count > capacity ? ~0ull : carry[0];
+}
+
+static int launch_var1(int type, const EncodeArgs& a, const Var1Bufs& v)
+{
+  cudaError_t e;
+  switch (type) {
+    case T_INT32: e = launch_encode_var1_t<T_INT32>(a, v); break;
+    case T_INT64: e = launch_encode_var1_t<T_INT64>(a, v); break;
+    case T_FLOAT: e = launch_encode_var1_t<T_FLOAT>(a, v); break;
+    case T_DOUBLE: e = launch_encode_var1_t<T_DOUBLE>(a, v); break;
+    default: return ZFP_B200_EINVAL;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return cuda_ok(e, "single-pass encode launch") ? ZFP_B200_OK : ZFP_B200_ECUDA;
+}
+
+// hand over from the single pass to the slot path: the running end becomes the cursor and the partial word the
+// single pass keeps in its carry is written out (upper bits zero), as clear_word_tail leaves it
+__global__ void carry_to_cursor(const unsigned long long* carry, uint64_t* words, uint64_t* cursor_out)
+{
+  const unsigned long long end = carry[0], tail = carry[1];
+  const uint32_t r = (uint32_t)(end & 63);
+  if (r) words[end >> 6] = tail >> (64 - r);
+  cursor_out[0] = end;
+  cursor_out[1] = end;
+  cursor_out[2] = 0;
+}
+
+// 3-D variable rate in one pass.  Synchronous calls first probe 64 Ki blocks: data whose blocks mostly outgrow the
+// shared-memory window (noise at tight tolerances, reversible mode on 64-bit types) would be coded twice, so for
+// them *resume is set to the block where the slot path takes over (the cursor scratch holds the position).
+// Stream-ordered calls (d_end_bit) cannot look and take the single pass throughout; an overflow list that runs
+// full is reported as an end position of ~0.
+static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm, const void* d_data, void* d_words,
+                       uint64 start_bit, uint64* end_bit, uint64* d_end_bit, zfp_b200_index* index, cudaStream_t st,
+                       uint64_t* resume)
+{
+  const int type = d->type;
+  int tile = 128;
+  switch (type) {
+    case T_INT32: tile = var1_tile_blocks<T_INT32>(); break;
+    case T_INT64: tile = var1_tile_blocks<T_INT64>(); break;
+    case T_FLOAT: tile = var1_tile_blocks<T_FLOAT>(); break;
+    default: tile = var1_tile_blocks<T_DOUBLE>(); break;
+  }
+  *resume = g.nblocks;
+  const uint64_t probe = d_end_bit ? 0 : (g.nblocks > 262144 ? 65536 : 0);
+  const uint64_t tiles = (g.nblocks - probe + tile - 1) / tile + 1;
+  uint64_t cap = g.nblocks / 16 + 4096;
+  if (cap > ((uint64_t)1 << 24)) cap = (uint64_t)1 << 24;
+  uint16_t* lengths;
+  if (index) {
+    if (!index_reserve(index, g.nblocks)) return ZFP_B200_ECUDA;
+    lengths = index->d_lengths;
+  }
+  else
+    lengths = static_cast<uint16_t*>(scratch(SCR_LENGTHS, g.nblocks * sizeof(uint16_t)));
+  // {ticket, overflow count} + status in one buffer; overflow list; carry (the cursor scratch)
+  char* stat = static_cast<char*>(scratch(SCR_TILES, tiles * 16 + 16));
+  void* list = scratch(SCR_OFFSETS, cap * 16);
+  unsigned long long* carry = static_cast<unsigned long long*>(scratch(SCR_CURSOR, 64));
+  if (!lengths || !stat || !list || !carry) return ZFP_B200_ECUDA;
+  init_carry<<<1, 1, 0, st>>>(carry, static_cast<const uint64_t*>(d_words), start_bit);
+  LAUNCHED();
+  Var1Bufs v;
+  v.status = stat + 16;
+  v.ticket = reinterpret_cast<unsigned int*>(stat);
+  v.overflow_count = reinterpret_cast<unsigned int*>(stat) + 1;
+  v.carry = carry;
+  v.overflow = list;
+  v.overflow_capacity = (unsigned int)cap;
+  v.sms = sm_count();
+  v.cleanup = 0;
+  CU(cudaMemsetAsync(stat, 0, 16, st));
+  EncodeArgs a = { d_data, g, prm, d_words, start_bit, 0, lengths, 0, g.nblocks, st, 1 };
+  int rc;
+  bool handover = false;
+  if (probe) {
+    CU(cudaMemsetAsync(stat + 16, 0, ((probe + tile - 1) / tile) * 16, st));
+    a.b1 = probe;
+    if ((rc = launch_var1(type, a, v))) return rc;
+    unsigned int h[2];
+    CU(cudaMemcpyAsync(h, stat, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    handover = (uint64_t)h[1] * 16 > probe;
+    a.b0 = probe;
+    a.b1 = g.nblocks;
+  }
+  if (!handover) {
+    CU(cudaMemsetAsync(stat, 0, 4, st));  // tickets start over, the overflow count runs on
+    CU(cudaMemsetAsync(stat + 16, 0, ((a.b1 - a.b0 + tile - 1) / tile) * 16, st));
+    if ((rc = launch_var1(type, a, v))) return rc;
+  }
+  else {
+    uint64_t* cursor = reinterpret_cast<uint64_t*>(carry) + 4;  // (the slot path's cursor lives behind the carry)
+    carry_to_cursor<<<1, 1, 0, st>>>(carry, static_cast<uint64_t*>(d_words), cursor);
+    LAUNCHED();
+    *resume = probe;
+  }
+  v.cleanup = 1;
+  if ((rc = launch_var1(type, a, v))) return rc;
+  if (index) {
+    index->keyed = true;
+    index->key_desc = *d;
+    index->key_start = start_bit;
+    index->total_bits = 0;
+  }
+  if (handover)
+    return ZFP_B200_OK;
+  if (d_end_bit) {  // stream-ordered: the size stays on the device
+    finish_async_var1<<<1, 1, 0, st>>>(d_end_bit, carry, v.overflow_count, v.overflow_capacity);
+    LAUNCHED();
+    return ZFP_B200_OK;
+  }
+  unsigned long long h_end = 0;
+  unsigned int h_cnt[2];
+  CU(cudaMemcpyAsync(&h_end, carry, sizeof(h_end), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_cnt, stat, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (h_cnt[1] > cap) {
+    // more long blocks than the list holds (the probe saw few): start over on the slot path
+    *resume = 0;
+    return ZFP_B200_OK;
+  }
+  if (end_bit) *end_bit = h_end;
+  if (index) index->total_bits = h_end - start_bit;
+  return ZFP_B200_OK;
+}
+
 // d_end_bit != nullptr: the end position is left in DEVICE memory and nothing synchronises the stream
 // (variable rate: the host never learns the size; the index's total_bits stays 0)
 static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words, uint64 start_bit,
@@ -448,6 +589,18 @@ static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words
     return ZFP_B200_OK;
   }
 
+  // variable rate, 3-D, on request (ZFP_B200_VAR1=1): one pass (kernels_var1.cuh) - encode, decoupled look-back,
+  // shifted plain stores.  Bit-exact and without the slot scratch, but measured SLOWER than the slot path below on
+  // the B200 (1024^3 fp64 accuracy 1e-6: 6.39 ms against 5.78 ms), so it is not the default.
+  static const bool single_pass = getenv("ZFP_B200_VAR1") != nullptr;
+  uint64_t first_block = 0;
+  bool resumed = false;
+  if (dims == 3 && single_pass) {
+    rc = encode_var1(d, g, prm, d_data, d_words, start_bit, end_bit, d_end_bit, index, st, &first_block);
+    if (rc || first_block >= g.nblocks) return rc;
+    resumed = first_block != 0;  // the slot path continues where the single pass handed over (0: it starts over)
+  }
+
   // variable rate: encode into per-block scratch slots, scan the lengths, compact bit-granularly
   const uint32_t slot_words = (block_capacity_bits(d) + 63) / 64 + 4;  // + room for a plane of overshoot past the budget
   const uint64_t slot_bytes = (uint64_t)slot_words * 8;
@@ -468,12 +621,15 @@ static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words
   uint64_t* offsets = static_cast<uint64_t*>(scratch(SCR_OFFSETS, chunk * 8));
   uint64_t* cursor = static_cast<uint64_t*>(scratch(SCR_CURSOR, 64));
   if (!lengths || !slots || !tiles || !offsets || !cursor) return ZFP_B200_ECUDA;
-
-  set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
-  LAUNCHED();
-  clear_word_tail<<<1, 1, 0, st>>>(static_cast<uint64_t*>(d_words), start_bit);
-  LAUNCHED();
-  for (uint64_t b0 = 0; b0 < g.nblocks; b0 += chunk) {
+  if (resumed)
+    cursor += 4;  // left there by carry_to_cursor, with the partial word already in place
+  else {
+    set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
+    LAUNCHED();
+    clear_word_tail<<<1, 1, 0, st>>>(static_cast<uint64_t*>(d_words), start_bit);
+    LAUNCHED();
+  }
+  for (uint64_t b0 = first_block; b0 < g.nblocks; b0 += chunk) {
     const uint64_t b1 = b0 + chunk < g.nblocks ? b0 + chunk : g.nblocks, cn = b1 - b0;
     rc = encode_any(2, type, dims, d_data, g, prm, slots, 0, slot_words, lengths, b0, b1, st);
     if (rc) return rc;

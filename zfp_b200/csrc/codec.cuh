@@ -166,15 +166,19 @@ struct ColWriter {
   // leave for the block's slot in global memory (gdst) and `drained` counts their bits
   uint32_t* gdst;
   uint32_t drained, cap;
+  // single-pass variable rate (kernels_var1.cuh): no slot - a block that outgrows the window just counts
+  // its bits (`drained` > 0 afterwards marks it) and is encoded again, in place, by the clean-up kernel
+  bool sink;
 
-  __device__ __forceinline__ void init(uint32_t* column, uint32_t* slot = nullptr, uint32_t capacity_words = 0)
+  __device__ __forceinline__ void init(uint32_t* column, uint32_t* slot = nullptr, uint32_t capacity_words = 0, bool count_only = false)
   {
     base = (uint32_t)__cvta_generic_to_shared(column);
     acc = 0;
     bp = 0;
-    gdst = slot;
+    gdst = count_only ? reinterpret_cast<uint32_t*>(8) : slot;  // (non-null: the window logic is on; never dereferenced)
     drained = 0;
     cap = capacity_words;
+    sink = count_only;
   }
   // call at plane boundaries: a plane appends < 200 bits and an append stores two words ahead
   __device__ __forceinline__ void drain_if_low()
@@ -184,14 +188,21 @@ struct ColWriter {
   }
   __device__ __forceinline__ void drain(uint32_t nwords)
   {
-    for (uint32_t j = 0; j < nwords; j++) {
-      uint32_t v;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (j << 7)));
-      gdst[j] = v;
+    if (!sink) {
+      for (uint32_t j = 0; j < nwords; j++) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (j << 7)));
+        gdst[j] = v;
+      }
+      gdst += nwords;
     }
-    gdst += nwords;
     drained += nwords * 32;
     bp &= 31;  // the partial word lives in acc; the next append rewrites column word 0 from it
+  }
+  // single pass: the partial word joins the column, nothing leaves
+  __device__ __forceinline__ void finish_window()
+  {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(word_addr()), "r"(acc) : "memory");
   }
   // variable rate: everything (including the partial word) to the slot
   __device__ __forceinline__ void finish_slot()

@@ -9,6 +9,7 @@
 #include "kernels4d.cuh"
 #include "kernels_ws.cuh"
 #include "kernels_q4.cuh"
+#include "kernels_var1.cuh"
 
 namespace zb {
 
@@ -279,6 +280,37 @@ cudaError_t launch_decode_impl(int dims, int offs_mode, const DecodeArgs& a)
     case 41: return run_decode4<TYPE, 1>(a);
     default: return cudaErrorInvalidValue;
   }
+}
+
+template <int TYPE, bool REV>
+cudaError_t run_encode_var1(const EncodeArgs& a, const Var1Bufs& v)
+{
+  if (v.cleanup) {
+    auto again = reencode_kernel<TYPE, REV>;
+    constexpr size_t smem2 = plane_smem_bytes<TYPE, 3>();
+    cudaError_t e = allow_smem(again, smem2);
+    if (e != cudaSuccess) return e;
+    again<<<(unsigned)(v.sms * 4), kThreads, smem2, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.out,
+                                                             static_cast<const Var1Overflow*>(v.overflow), v.overflow_count, v.overflow_capacity);
+    return cudaGetLastError();
+  }
+  auto kernel = encode_var1_kernel<TYPE, REV>;
+  constexpr int threads = EncCfg<TYPE>::threads;
+  constexpr size_t smem = var_smem_bytes<TYPE, 3>() / (kThreads / 32) * (threads / 32);
+  cudaError_t e = allow_smem(kernel, smem);
+  if (e != cudaSuccess) return e;
+  const uint64_t ctas = (a.b1 - a.b0 + threads - 1) / threads;
+  kernel<<<(unsigned)ctas, threads, smem, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                    static_cast<uint64_t*>(a.out), a.lengths, a.b0, a.b1,
+                                                    static_cast<Var1Status*>(v.status), v.ticket, v.carry,
+                                                    static_cast<Var1Overflow*>(v.overflow), v.overflow_count, v.overflow_capacity);
+  return cudaGetLastError();
+}
+
+template <int TYPE>
+cudaError_t launch_encode_var1_impl(const EncodeArgs& a, const Var1Bufs& v)
+{
+  return a.prm.minexp < kMinExp ? run_encode_var1<TYPE, true>(a, v) : run_encode_var1<TYPE, false>(a, v);
 }
 
 template <int TYPE>

@@ -71,9 +71,25 @@ struct DecodeArgs {
   uint32_t* check;  // OFFS 1: set to non-zero by any block whose parsed length differs from lengths[b] (nullptr: no check)
 };
 
+// single-pass variable-rate encode (kernels_var1.cuh): device buffers of one launch
+struct Var1Bufs {
+  void* status;                   // Var1Status[tiles], zeroed
+  unsigned int* ticket;           // zeroed
+  unsigned long long* carry;      // {end position, last 64 bits} before this launch; updated by it
+  void* overflow;                 // Var1Overflow[overflow_capacity]
+  unsigned int* overflow_count;   // accumulates over the launches of one array
+  unsigned int overflow_capacity;
+  int sms;                        // multiprocessors (grid of the clean-up kernel)
+  int cleanup;                    // 0: encode blocks [b0, b1) only; 1: only run the clean-up kernel
+};
+
 // one translation unit per scalar type and direction (inst_*.cu) defines these
 template <int TYPE> cudaError_t launch_encode_t(int dims, int out_mode, const EncodeArgs& a);
 template <int TYPE> cudaError_t launch_decode_t(int dims, int offs_mode, const DecodeArgs& a);
+// 3-D, variable rate: encode + place blocks [a.b0, a.b1) in one pass, then re-encode the overflowing ones; returns
+// the tile size through *tile_blocks when a == nullptr-like query is wanted (see backend.cu)
+template <int TYPE> cudaError_t launch_encode_var1_t(const EncodeArgs& a, const Var1Bufs& v);
+template <int TYPE> int var1_tile_blocks();
 // sequential rebuild of the block-length index of a variable-rate stream
 template <int TYPE> cudaError_t launch_index_t(int dims, const DecodeArgs& a, uint16_t* lengths);
 
