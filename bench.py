@@ -201,6 +201,21 @@ def host_field(side):
     return out.numpy()
 
 
+def time_parallel_decompress(words, a, threads):
+    """Row f4 (oracle/ref_parallel_decompress.c): chunk-parallel fixed-rate decompress around the reference's block
+    API; GB/s of uncompressed data, or None when the helper library is not built."""
+    try:
+        from oracle.oracle import parallel_decompress
+        out = np.empty_like(a)
+        w = np.concatenate([words, np.zeros(2, dtype=np.uint64)])
+        parallel_decompress(w, a.shape, a.dtype, RATE * 64, threads, out=out)
+        t0 = time.perf_counter()
+        parallel_decompress(w, a.shape, a.dtype, RATE * 64, threads, out=out)
+        return a.nbytes / (time.perf_counter() - t0) / 1e9
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """The reference's own CPU implementation on the box's host cores, SAME configuration as our arm: the full
     1024^3 fp64 slab at rate 8 per step (zfp_exec_omp compress with all threads + serial decompress - upstream
@@ -220,7 +235,8 @@ def run_reference(args):
     if args.quick:
         side = 256
     a = host_field(side) if side == SIDE else cpu_sample_field(side)
-    tc, td, _, _ = time_reference(a, args.steps, args.warmup, threads)
+    tc, td, ref_words, _ = time_reference(a, args.steps, args.warmup, threads)
+    pdec = time_parallel_decompress(ref_words, a, threads)
     step = float(np.sum(tc) + np.sum(td)) / args.steps
     value = 2 * a.nbytes / step / 1e9
     same = side == SIDE
@@ -234,7 +250,9 @@ def run_reference(args):
                              "%d^3 sub-box of the same analytic field per step (host memory too small for the full slab)" % side},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
                          "sample": "%d x %d x %d fp64 (%.2f GiB) per step; zfp_exec_omp compress with %d threads (%.3f GB/s) + serial decompress (%.3f GB/s; reference has no parallel decompress)"
-                                   % (a.shape[0], a.shape[1], a.shape[2], a.nbytes / 2 ** 30, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9)},
+                                   % (a.shape[0], a.shape[1], a.shape[2], a.nbytes / 2 ** 30, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9),
+                         "chunk_parallel_decompress_gbs": pdec,
+                         "chunk_parallel_note": "not part of `value`: an OpenMP driver of ours around the reference's block API (oracle/ref_parallel_decompress.c, scope row f4), what upstream announces in docs/source/execution.rst:302-304"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -627,6 +645,7 @@ def run_ours(args):
             a = x[:side, :side, :side].contiguous().cpu().numpy()
             tc, td, ref_words, ref_out = time_reference(a, 2, 1, threads)
             tcs, tds, _, _ = time_reference(a[: side // 2], 1, 0, 1)
+            pdec = time_parallel_decompress(ref_words, a, threads)
             cs = zb.compress(torch.from_numpy(a).to(dev), **mode)
             parity = cs.to_numpy().tobytes() == ref_words.tobytes() and zb.decompress(cs).cpu().numpy().tobytes() == ref_out.tobytes()
             val = 2 * a.nbytes / (np.mean(tc) + np.mean(td)) / 1e9
@@ -634,6 +653,7 @@ def run_ours(args):
                 "value": val, "unit": UNIT, "cores": threads, "kind": "reference",
                 "sample": "%d^3 sub-box of the bench field; zfp_exec_omp compress x%d threads %.3f GB/s + serial decompress %.3f GB/s (no parallel decompress upstream); serial compress %.3f GB/s on half the sample"
                           % (side, threads, a.nbytes / np.mean(tc) / 1e9, a.nbytes / np.mean(td) / 1e9, a.nbytes / 2 / np.mean(tcs) / 1e9),
+                "chunk_parallel_decompress_gbs": pdec,
                 "stream_and_array_bit_identical_to_gpu": bool(parity)}
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "error": repr(ex)[:200]}

@@ -29,6 +29,7 @@ ZFP_MAX_BITS = 16658
 
 
 REF_CUDA_SO = os.path.join(HERE, "_ref", "libzfp_ref_cuda.so")
+REF_PDEC_SO = os.path.join(HERE, "_ref", "libzfp_ref_pdec.so")  # chunk-parallel fixed-rate CPU decompress (row f4)
 REF_CUDA_ALL_SO = os.path.join(HERE, "_ref", "libzfp_ref_cuda_all.so")    # reference + integration/zfp_cuda_dispatch.patch on our backend
 REF_CUDA_ORIG_SO = os.path.join(HERE, "_ref", "libzfp_ref_cudaorig.so")   # reference with ITS OWN src/cuda_zfp (the backend replaced)
 
@@ -36,7 +37,7 @@ REF_CUDA_ORIG_SO = os.path.join(HERE, "_ref", "libzfp_ref_cudaorig.so")   # refe
 def build(ref=True):
     """(Re)build the oracle libraries with oracle/Makefile."""
     have_ref = ref and os.path.isdir(os.environ.get("ZFP_REFERENCE", "/root/reference"))
-    targets = ["port"] + (["ref"] if have_ref else [])
+    targets = ["port"] + (["ref", "ref_pdec"] if have_ref else [])
     if have_ref and os.path.exists(os.path.join(HERE, "..", "zfp_b200", "lib", "libzfp_b200.so")):
         targets += ["ref_cuda", "ref_cli", "ref_cuda_all", "ref_cudaorig", "b200_cli"]
     subprocess.check_call(["make", "-s", "-C", HERE] + targets)
@@ -364,6 +365,23 @@ class Reference:
         out = np.empty(shape, dtype=dtype)
         self.decompress_raw(words, out.reshape(-1), 0, dtype, _shape_to_n(shape), None, mode)
         return out
+
+
+def parallel_decompress(words, shape, dtype, maxbits, threads, out=None, start_bit=0):
+    """Chunk-parallel FIXED-RATE decompression on the host: oracle/ref_parallel_decompress.c,
+    an OpenMP driver around the reference's own block API, for the CPU column of the baseline table."""
+    if not os.path.exists(REF_PDEC_SO):
+        raise FileNotFoundError(REF_PDEC_SO + " (run `make -C oracle ref_pdec` where /root/reference exists)")
+    L = C.CDLL(REF_PDEC_SO)
+    L.zfp_ref_parallel_decompress.restype = C.c_uint64
+    L.zfp_ref_parallel_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.POINTER(C.c_size_t), C.c_uint,
+                                              C.c_void_p, C.c_int]
+    out = np.empty(shape, dtype=dtype) if out is None else out
+    n = (C.c_size_t * 4)(*(list(reversed(shape)) + [0] * (4 - len(shape))))
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    used = L.zfp_ref_parallel_decompress(words.ctypes.data, words.nbytes, start_bit, ZFP_TYPE[np.dtype(dtype)], n, int(maxbits),
+                                         out.ctypes.data, int(threads))
+    return out, int(used)
 
 
 class RefTestUtils:

@@ -130,3 +130,24 @@ def test_param_setters_match_reference(port, ref):
                 for n in ([17, 0, 0, 0], [17, 5, 0, 0], [17, 5, 9, 0], [17, 5, 9, 6]):
                     if sum(1 for v in n if v) == dims:
                         assert port.maximum_size(mode, dtype, n) == ref.maximum_size(mode, dtype, n)
+
+
+def test_parallel_cpu_decompress_equals_serial(ref):
+    """Row f4 of the scope table: the chunk-parallel fixed-rate CPU decompress (an OpenMP driver around the
+    reference's own block API, oracle/ref_parallel_decompress.c) reproduces the reference's serial
+    zfp_decompress bit for bit - every type, 1-4 D, partial blocks, 1 and 4 threads."""
+    from oracle.oracle import REF_PDEC_SO, parallel_decompress
+    if not os.path.exists(REF_PDEC_SO):
+        pytest.skip("oracle/_ref/libzfp_ref_pdec.so not built")
+    for dtype in (np.float32, np.float64, np.int32, np.int64):
+        for shape in ((37,), (14, 19), (9, 10, 13), (5, 6, 7, 9)):
+            a = make_field(shape, dtype, seed=17, kind="smooth")
+            for rate in (4, 9.5, 20):
+                mode = {"rate": rate}
+                words = ref.compress(a, **mode)
+                want = ref.decompress(words, a.shape, a.dtype, **mode)
+                maxbits = ref.params(mode, a.dtype, a.ndim)[1]
+                for threads in (1, 4):
+                    got, used = parallel_decompress(np.concatenate([words, np.zeros(2, dtype=np.uint64)]), a.shape, a.dtype, maxbits, threads)
+                    assert got.tobytes() == want.tobytes(), (np.dtype(dtype).name, shape, rate, threads)
+                    assert (used + 63) // 64 * 8 == words.nbytes

@@ -48,9 +48,12 @@ def _compile(src, obj, verbose):
 
 def build_library(force=False, verbose=False, jobs=None):
     """Compile the CUDA backend + host API into zfp_b200/lib/libzfp_b200.so; returns its path."""
-    os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     newest_header = max(os.path.getmtime(h) for h in _headers())
+    # an up-to-date library is enough (the object files do not travel to the GPU box)
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max([newest_header] + [os.path.getmtime(f) for f in _sources()]):
+        return LIB
+    os.makedirs(OBJ_DIR, exist_ok=True)
     todo, objs = [], []
     for src in _sources():
         obj = os.path.join(OBJ_DIR, os.path.basename(src) + ".o")

@@ -1614,7 +1614,17 @@ template <class W> struct is_lockstep<W, std::enable_if_t<W::kLockstep>> : std::
 // whole-block encode / decode for one thread.  `sp` is the lane's plane column in shared memory.
 // Returns the number of bits the block occupies in the stream.
 // ------------------------------------------------------------------------------------------------
-template <int TYPE, int DIMS, bool REV, class Writer>
+// SYNC_THREADS > 0 (developer experiment, fixed-rate staged kernel with large CTAs only): the warps that share a
+// scheduler (warp, warp + 4, ...; SYNC_THREADS of them in threads) meet at a named barrier before each long
+// straight-line stage, so that they walk it together and one instruction fetch serves them all
+template <int SYNC_THREADS>
+__device__ __forceinline__ void stage_rendezvous()
+{
+  if constexpr (SYNC_THREADS > 0)
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + ((threadIdx.x >> 5) & 3)), "n"(SYNC_THREADS) : "memory");
+}
+
+template <int TYPE, int DIMS, bool REV, class Writer, int SYNC_THREADS = 0>
 __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Scalar (&v)[1 << (2 * DIMS)],
                                                  const Params& prm, Writer& bw,
                                                  typename PlaneWord<(1 << (2 * DIMS))>::type* sp)
@@ -1694,6 +1704,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   // lossy modes: u holds q + 0xaaaa..., the XOR half of int2uint happens inside the plane transposes
   constexpr int NEG = REV ? 0 : 1;
   if (!reversible) {
+    stage_rendezvous<SYNC_THREADS>();
     xform_fwd<0, DIMS>(q);
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -1744,6 +1755,7 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
       // blocks that stop within the high half (accuracy 1e-6, precision 32) are fastest with an
       // undivided half, blocks that go a few planes further (rate 8) with a 16-plane window.
       if (st.k > 32) {
+        stage_rendezvous<SYNC_THREADS>();
         const int kup = to_planes_half<1, NEG, UInt, N>(u, sp);
         encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp, 32 + kup);
       }

@@ -221,6 +221,9 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_ENC64_THREADS
 #define ZB_ENC64_THREADS 128
 #endif
+#ifndef ZB_ENC_SYNC
+#define ZB_ENC_SYNC 0  // 1 with ZB_ENC64_THREADS = 256 / 384: warps on one scheduler rendezvous before the long stages
+#endif
 template <int TYPE> struct EncCfg {
   static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_ENC64_THREADS : kThreads;
   static constexpr int min_ctas(bool rev)
@@ -262,7 +265,11 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 
   ColWriter bw;
   bw.init(stage);
+#if ZB_ENC_SYNC
+  encode_block<TYPE, DIMS, REV, ColWriter, (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) ? EncCfg<TYPE>::threads / 4 : 0>(v, prm, bw, sp);
+#else
   encode_block<TYPE, DIMS, REV>(v, prm, bw, sp);
+#endif
   bw.finish(words);
 
   if (valid) {

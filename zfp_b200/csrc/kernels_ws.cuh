@@ -53,6 +53,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity)
 template <int REGS> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
 
+#ifndef ZB_WS_SYNC
+#define ZB_WS_SYNC 1
+#endif
 // ---- configuration -------------------------------------------------------------------------------
 constexpr int kWsPairs = 4;                  // parse/tail warp pairs per CTA (one warpgroup each side)
 constexpr int kWsThreads = 64 * kWsPairs;    // 256
@@ -151,10 +154,13 @@ decode_ws_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Param
   const uint64_t stride = (uint64_t)gridDim.x * kWsPairs;
   uint32_t q = 0;  // windows produced / consumed so far by this pair
 
+  // every pair of the CTA makes the same number of trips (pair 0's), so that the tail warps can meet at a named
+  // barrier before each tail; a trip past the last batch parses the last batch again and stores nothing
   if (parser) {
     reg_dealloc<kWsParseRegs>();
     uint32_t* stage = column + lane;
-    for (uint64_t t = (uint64_t)blockIdx.x * kWsPairs + pair; t < nbatches; t += stride) {
+    for (uint64_t t0 = (uint64_t)blockIdx.x * kWsPairs; t0 < nbatches; t0 += stride) {
+      const uint64_t t = t0 + pair < nbatches ? t0 + pair : nbatches - 1;
       const uint64_t b_raw = block0 + t * 32 + lane;
       const uint64_t b = b_raw < block1 ? b_raw : block1 - 1;  // lanes past the end redo the last block (warp votes need 32 lanes)
       // the block's words into the lane's column, all loads in flight
@@ -219,9 +225,11 @@ decode_ws_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Param
   }
   else {
     reg_alloc<kWsTailRegs>();
-    for (uint64_t t = (uint64_t)blockIdx.x * kWsPairs + pair; t < nbatches; t += stride) {
+    for (uint64_t t0 = (uint64_t)blockIdx.x * kWsPairs; t0 < nbatches; t0 += stride) {
+      const bool real = t0 + pair < nbatches;
+      const uint64_t t = real ? t0 + pair : nbatches - 1;
       const uint64_t b_raw = block0 + t * 32 + lane;
-      const bool valid = b_raw < block1;
+      const bool valid = real && b_raw < block1;
       const uint64_t b = valid ? b_raw : block1 - 1;
       UInt u[N];
 #pragma unroll
@@ -248,6 +256,10 @@ decode_ws_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Param
         q++;
         if (last) break;
       }
+#if ZB_WS_SYNC
+      // the four tail warps of the CTA walk the long straight-line tail together: one instruction fetch serves four
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kWsPairs) : "memory");
+#endif
       // inverse negabinary (the XOR half happened in the transposes), order, lifting, cast, scatter
       Int qv[N];
 #pragma unroll
