@@ -129,6 +129,48 @@ def test_long_blocks_and_noisy_planes(zb, port, dtype, shape):
             assert back.tobytes() == port.decompress(want, a.shape, a.dtype, **mode).tobytes(), mode
 
 
+def _arbitrary_stream(nblocks, maxbits, ebits, ebias, seed):
+    """Fixed-rate stream (maxbits a multiple of 64) whose blocks are random bit soup of varying density
+    behind a sane header: '1' + an exponent near the bias.  Any bit pattern is a legal block."""
+    from helpers import splitmix64
+    wpb = maxbits // 64
+    n = nblocks * wpb
+    r = [splitmix64(np.arange(n, dtype=np.uint64), seed + 7919 * j) for j in range(4)]
+    dens = (splitmix64(np.arange(nblocks, dtype=np.uint64), seed + 5) % np.uint64(5)).repeat(wpb)
+    w = r[0].copy()
+    w = np.where(dens >= 1, w & r[1], w)
+    w = np.where(dens >= 2, w & r[2], w)
+    w = np.where(dens >= 3, w & r[3], w)
+    w = np.where(dens >= 4, w & (r[1] >> np.uint64(7)) & (r[2] << np.uint64(9)), w)
+    head = w.reshape(nblocks, wpb)
+    if ebits:
+        e = (splitmix64(np.arange(nblocks, dtype=np.uint64), seed + 3) % np.uint64(40)).astype(np.int64) - 20 + ebias
+        hdr_mask = np.uint64((1 << (1 + ebits)) - 1)
+        head[:, 0] = (head[:, 0] & ~hdr_mask) | np.uint64(1) | (e.astype(np.uint64) << np.uint64(1))
+    return head.reshape(-1)
+
+
+@pytest.mark.parametrize("dtype,shape,rates", [(np.float64, (36, 40, 44), (1, 2, 4, 8, 16, 32)), (np.float64, (70, 66), (4, 8, 16, 32)),
+                                               (np.float64, (1000,), (16, 32, 64)), (np.float32, (36, 40, 44), (1, 2, 4, 8, 16)),
+                                               (np.int64, (33, 32, 36), (1, 2, 4, 8, 16)), (np.int32, (70, 66), (4, 8, 16))])
+def test_decode_of_arbitrary_bit_streams(zb, port, dtype, shape, rates):
+    """The decoder against the oracle on streams no encoder produced: random bits of several densities
+    decode to coefficients anywhere in the 64-bit range, so the inverse transform wraps around in
+    int64 in some blocks and not in others - the FP64-pipe tail of the fp64 kernels must tell the two
+    apart (its range bound) and agree with the integer arithmetic of the reference bit for bit."""
+    dt = np.dtype(dtype)
+    ebits, ebias = {"float64": (11, 1023), "float32": (8, 127)}.get(dt.name, (0, 0))
+    nblocks = int(np.prod([(n + 3) // 4 for n in shape]))
+    for rate in rates:
+        maxbits = rate * 4 ** len(shape)
+        assert maxbits % 64 == 0
+        for seed in (1, 2):
+            words = _arbitrary_stream(nblocks, maxbits, ebits, ebias, 1000 * rate + seed)
+            got, _ = zb.decompress_numpy(words, shape, dt, rate=rate)
+            want = port.decompress(words, shape, dt, rate=rate)
+            assert got.tobytes() == want.tobytes(), (dt.name, shape, rate, seed)
+
+
 @pytest.mark.parametrize("dtype,shape,rate", [(np.float32, (262, 256, 256), 8), (np.float64, (70, 512, 500), 4),
                                               (np.float32, (5000, 4100), 16), (np.float64, (9000001,), 8)])
 def test_host_buffers_slab_pipeline(zb, dtype, shape, rate):

@@ -34,6 +34,9 @@
 namespace zb {
 
 // developer switch for A/B timing: 0 removes the narrow (32-bit) plane steps of the 64-value coders
+#ifndef ZB_FP64_TAIL
+#define ZB_FP64_TAIL 1  // inverse transform of fp64 blocks on the FP64 pipe where that is exact (decode_block)
+#endif
 #ifndef ZB_NARROW
 #define ZB_NARROW 0
 #endif
@@ -478,6 +481,52 @@ __device__ __forceinline__ void xform_inv(Int (&p)[1 << (2 * DIMS)])
   lift_axis<KIND, DIMS, 0>(p);
 }
 
+// The inverse transform of 64-bit coefficients on the FP64 pipe (decode only).  A block whose lowest
+// decoded plane is L has coefficients that are multiples of 2^L; one inv_lift halves twice
+// ("y += w >> 1; w -= y >> 1", decode.c:13-45 of the reference's template), so after d passes every
+// intermediate is still a multiple of 2^(L-2d): no shift ever drops a bit and the arithmetic is
+// plain linear algebra over the integers.  While nothing leaves the int64 range the values are also
+// doubles with at most 63 - (L - 2d) <= 53 significant bits when L >= 10 + 2d: each step is then ONE
+// exact DADD / DFMA instead of two to four instructions on the integer pipe, and the result equals
+// the integer transform bit for bit (wrapping can only matter where a shift or the final conversion
+// looks at a wrapped value; lift_gain() bounds every such value, see decode_block).
+__device__ __forceinline__ void inv_lift_f64(double& x, double& y, double& z, double& w)
+{
+  y = __fma_rn(w, 0.5, y); w = __fma_rn(y, -0.5, w);
+  y = __dadd_rn(y, w); w = __fma_rn(w, 2.0, -y);
+  z = __dadd_rn(z, x); x = __fma_rn(x, 2.0, -z);
+  y = __dadd_rn(y, z); z = __fma_rn(z, 2.0, -y);
+  w = __dadd_rn(w, x); x = __fma_rn(x, 2.0, -w);
+}
+template <int DIMS, int AXIS>
+__device__ __forceinline__ void inv_lift_axis_f64(double (&p)[1 << (2 * DIMS)])
+{
+  constexpr int N = 1 << (2 * DIMS), st = 1 << (2 * AXIS);
+#pragma unroll
+  for (int i = 0; i < N; i++)
+    if (((i >> (2 * AXIS)) & 3) == 0)
+      inv_lift_f64(p[i], p[i + st], p[i + 2 * st], p[i + 3 * st]);
+}
+template <int DIMS>
+__device__ __forceinline__ void xform_inv_f64(double (&p)[1 << (2 * DIMS)])
+{
+  if (DIMS > 2) inv_lift_axis_f64<DIMS, (DIMS > 2 ? 2 : 0)>(p);
+  if (DIMS > 1) inv_lift_axis_f64<DIMS, (DIMS > 1 ? 1 : 0)>(p);
+  inv_lift_axis_f64<DIMS, 0>(p);
+}
+// Largest magnitude with which coefficient i (natural order) enters any value the inverse transform
+// shifts or returns: per axis the largest entry of its column over the rows y + w/2 (the shifted
+// intermediate) and the four outputs (x, y, z, w columns: 1, 3/2, 1, 5/4), multiplied over the axes.
+__host__ __device__ constexpr double lift_gain(int i, int dims)
+{
+  double g = 1;
+  for (int d = 0; d < dims; d++) {
+    const int j = (i >> (2 * d)) & 3;
+    g *= j == 1 ? 1.5 : (j == 3 ? 1.25 : 1.0);
+  }
+  return g;
+}
+
 // ------------------------------------------------------------------------------------------------
 // 32x32 bit-matrix transpose in registers: on return bit i of a[j] is the former bit j of a[i]
 // ------------------------------------------------------------------------------------------------
@@ -599,7 +648,7 @@ template <int NEG> struct NegaWord {
 };
 
 // coefficients (sequency order) -> bit planes
-template <int NEG, class UInt, int N>
+template <int NEG, class UInt, int N, int STRIDE = 32>
 __device__ __forceinline__ void to_planes(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
 {
   constexpr int P = 8 * (int)sizeof(UInt);
@@ -617,15 +666,15 @@ __device__ __forceinline__ void to_planes(const UInt (&u)[N], typename PlaneWord
 #pragma unroll
     for (int k = 0; k < 32; k++) {
       if (G == 2)
-        sp[(32 * h + k) * 32] = (typename PlaneWord<N>::type)((uint64_t)a[0][k] | ((uint64_t)a[G - 1][k] << 32));
+        sp[(32 * h + k) * STRIDE] = (typename PlaneWord<N>::type)((uint64_t)a[0][k] | ((uint64_t)a[G - 1][k] << 32));
       else
-        sp[(32 * h + k) * 32] = (typename PlaneWord<N>::type)a[0][k];
+        sp[(32 * h + k) * STRIDE] = (typename PlaneWord<N>::type)a[0][k];
     }
   }
 }
 
 // bit planes -> coefficients; planes below kstop were never written and read as zero
-template <int NEG, class UInt, int N>
+template <int NEG, class UInt, int N, int STRIDE = 32>
 __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWord<N>::type* sp, int kstop)
 {
   constexpr int P = 8 * (int)sizeof(UInt);
@@ -638,7 +687,7 @@ __device__ __forceinline__ void from_planes(UInt (&u)[N], const typename PlaneWo
     uint32_t a[G][32];
 #pragma unroll
     for (int k = 0; k < 32; k++) {
-      typename PlaneWord<N>::type x = (32 * h + k >= kstop) ? sp[(32 * h + k) * 32] : 0;
+      typename PlaneWord<N>::type x = (32 * h + k >= kstop) ? sp[(32 * h + k) * STRIDE] : 0;
       a[0][k] = (uint32_t)x;
       if (G == 2)
         a[G - 1][k] = (uint32_t)((uint64_t)x >> 32);
@@ -1838,6 +1887,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
   }
 
   UInt u[N];
+  int lowest = 0;  // lowest plane this block decoded (lockstep readers; P when none)
   // lossy modes: the plane transposes deliver u ^ 0xaaaa... (the XOR half of uint2int); planes that
   // are never decoded leave the mask's bits
   constexpr int NEG = REV ? 0 : 2;
@@ -1893,6 +1943,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
       from_planes_half<0, NEG, UInt, N>(u, sp, st.lowest, N <= 32 || __any_sync(0xffffffffu, st.n > 32));
     }
     bits += budget - st.bits;
+    lowest = st.lowest;
   }
   else if (!zero) {
     int kstop;
@@ -1913,6 +1964,40 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
 #pragma unroll
   for (int i = 0; i < N; i++)
     q[perm_at<DIMS>(i)] = REV ? uint2int(u[i]) : (Int)(u[i] - (UInt)0xaaaaaaaaaaaaaaaaull);
+
+#if ZB_FP64_TAIL
+  if constexpr (TYPE == T_DOUBLE && !REV && DIMS <= 3 && is_lockstep<Reader>::value) {
+    // FP64-pipe tail (see inv_lift_f64): every block of the warp stopped at plane >= 10 + 2 DIMS, and
+    // the weighted sum of magnitudes proves that no shifted or returned value leaves the int64 range
+    constexpr uint32_t FULL = 0xffffffffu;
+    if (__all_sync(FULL, lowest >= 10 + 2 * DIMS)) {
+      double d[N];
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        d[i] = __ll2double_rn(q[i]);  // exact: a multiple of 2^lowest below 2^63
+#pragma unroll
+      for (int i = 0; i < N; i += 4) {
+        s0 = __fma_rn(fabs(d[i]), lift_gain(i, DIMS), s0);
+        s1 = __fma_rn(fabs(d[i + 1]), lift_gain(i + 1, DIMS), s1);
+        s2 = __fma_rn(fabs(d[i + 2]), lift_gain(i + 2, DIMS), s2);
+        s3 = __fma_rn(fabs(d[i + 3]), lift_gain(i + 3, DIMS), s3);
+      }
+      if (__all_sync(FULL, (s0 + s1) + (s2 + s3) < 0x1.fffffffp+62)) {
+        xform_inv_f64<DIMS>(d);
+        const double s = pow2<double>(emax - (TR::P - 2));
+#pragma unroll
+        for (int i = 0; i < N; i++)
+          v[i] = s * d[i];
+        return bits;
+      }
+      // back to integers for the general tail (exact both ways; q and d never live together)
+#pragma unroll
+      for (int i = 0; i < N; i++)
+        q[i] = __double2ll_rn(d[i]);
+    }
+  }
+#endif
   if (!reversible)
     xform_inv<1, DIMS>(q);
   else

@@ -7,6 +7,7 @@
 
 #include "kernels.cuh"
 #include "kernels4d.cuh"
+#include "kernels4q.cuh"
 #include "kernels_ws.cuh"
 #include "kernels_q4.cuh"
 #include "kernels_var1.cuh"
@@ -233,6 +234,17 @@ cudaError_t run_decode(const DecodeArgs& a)
 template <int TYPE, int OUT>
 cudaError_t run_encode4(const EncodeArgs& a)
 {
+  static const bool one_thread_per_block = getenv("ZFP_B200_4D_OLD") != nullptr;  // developer A/B switch
+  if (!one_thread_per_block) {
+    const unsigned ctas = (unsigned)((a.b1 - a.b0 + kBlocks4q - 1) / kBlocks4q);
+    const size_t smem = (size_t)kBlocks4q * block_bytes4q<TYPE>();
+    auto data = static_cast<const typename Traits<TYPE>::Scalar*>(a.data);
+    if (a.prm.minexp < kMinExp)
+      encode4q_kernel<TYPE, OUT, true><<<ctas, kThreads4q, smem, a.st>>>(data, a.g, a.prm, a.out, a.start_bit, a.slot_words, a.lengths, a.b0, a.b1);
+    else
+      encode4q_kernel<TYPE, OUT, false><<<ctas, kThreads4q, smem, a.st>>>(data, a.g, a.prm, a.out, a.start_bit, a.slot_words, a.lengths, a.b0, a.b1);
+    return cudaGetLastError();
+  }
   const unsigned ctas = (unsigned)((a.b1 - a.b0 + kThreads4 - 1) / kThreads4);
   encode4_kernel<TYPE, OUT><<<ctas, kThreads4, 0, a.st>>>(static_cast<const typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                            a.out, a.start_bit, a.slot_words, a.lengths, a.b0, a.b1);
@@ -242,6 +254,17 @@ cudaError_t run_encode4(const EncodeArgs& a)
 template <int TYPE, int OFFS>
 cudaError_t run_decode4(const DecodeArgs& a)
 {
+  static const bool one_thread_per_block = getenv("ZFP_B200_4D_OLD") != nullptr;
+  if (!one_thread_per_block) {
+    const unsigned ctas = (unsigned)((a.b1 - a.b0 + kBlocks4q - 1) / kBlocks4q);
+    const size_t smem = (size_t)kBlocks4q * block_bytes4q<TYPE>();
+    auto data = static_cast<typename Traits<TYPE>::Scalar*>(a.data);
+    if (a.prm.minexp < kMinExp)
+      decode4q_kernel<TYPE, OFFS, true><<<ctas, kThreads4q, smem, a.st>>>(data, a.g, a.prm, a.in, a.start_bit, a.offsets, a.b0, a.b1, a.lengths, a.check);
+    else
+      decode4q_kernel<TYPE, OFFS, false><<<ctas, kThreads4q, smem, a.st>>>(data, a.g, a.prm, a.in, a.start_bit, a.offsets, a.b0, a.b1, a.lengths, a.check);
+    return cudaGetLastError();
+  }
   const unsigned ctas = (unsigned)((a.b1 - a.b0 + kThreads4 - 1) / kThreads4);
   decode4_kernel<TYPE, OFFS><<<ctas, kThreads4, 0, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm, a.in,
                                                             a.start_bit, a.offsets, a.b0, a.b1, a.lengths, a.check);

@@ -158,13 +158,14 @@ __device__ uint32_t encode_planes4(Writer& bw, uint32_t budget, uint32_t maxprec
   return budget - bits;
 }
 
-template <int P>
+template <int P, bool ZERO = true>
 __device__ uint32_t decode_planes4(BitReader& br, uint32_t budget, uint32_t maxprec, uint32_t* pl)
 {
   const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
   uint32_t bits = budget, n = 0;
-  for (int i = 0; i < P * 8; i++)
-    pl[i] = 0;
+  if (ZERO)
+    for (int i = 0; i < P * 8; i++)
+      pl[i] = 0;
   for (int k = P - 1; bits && k >= kmin; k--) {
     uint32_t* x = pl + k * 8;
     uint32_t m = n < bits ? n : bits;
