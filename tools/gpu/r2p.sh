@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 200 python tools/quick_gpu_check.py 1024 2>&1 | grep -E 'mismatch|float64|Error|error' > gpurun_out/r2p_quick.txt
+cat gpurun_out/r2p_quick.txt
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2p_pytest.txt 2>&1
+tail -15 gpurun_out/r2p_pytest.txt

@@ -412,21 +412,11 @@ static int launch_var1(int type, const EncodeArgs& a, const Var1Bufs& v)
 
 // hand over from the single pass to the slot path: the running end becomes the cursor and the partial word the
 // single pass keeps in its carry is written out (upper bits zero), as clear_word_tail leaves it
-__global__ void carry_to_cursor(const unsigned long long* carry, uint64_t* words, uint64_t* cursor_out)
-{
-  const unsigned long long end = carry[0], tail = carry[1];
-  const uint32_t r = (uint32_t)(end & 63);
-  if (r) words[end >> 6] = tail >> (64 - r);
-  cursor_out[0] = end;
-  cursor_out[1] = end;
-  cursor_out[2] = 0;
-}
-
-// 3-D variable rate in one pass.  Synchronous calls first probe 64 Ki blocks: data whose blocks mostly outgrow the
-// shared-memory window (noise at tight tolerances, reversible mode on 64-bit types) would be coded twice, so for
-// them *resume is set to the block where the slot path takes over (the cursor scratch holds the position).
-// Stream-ordered calls (d_end_bit) cannot look and take the single pass throughout; an overflow list that runs
-// full is reported as an end position of ~0.
+// 3-D variable rate in one pass.  Blocks that outgrow the shared-memory window leave a hole and are coded again
+// by the clean-up launch; when there are more of them than the overflow list holds (noise at tight tolerances)
+// a synchronous call starts over on the slot path (*resume = 0), a stream-ordered call (d_end_bit) reports an
+// end position of ~0.  (A probe of the first 64 Ki blocks with a hand-over to the slot path in mid-stream was
+// tried and removed: it lost streams of long blocks at 290 K blocks and the path is slower anyway.)
 static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm, const void* d_data, void* d_words,
                        uint64 start_bit, uint64* end_bit, uint64* d_end_bit, zfp_b200_index* index, cudaStream_t st,
                        uint64_t* resume)
@@ -440,8 +430,7 @@ static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm,
     default: tile = var1_tile_blocks<T_DOUBLE>(); break;
   }
   *resume = g.nblocks;
-  const uint64_t probe = d_end_bit ? 0 : (g.nblocks > 262144 ? 65536 : 0);
-  const uint64_t tiles = (g.nblocks - probe + tile - 1) / tile + 1;
+  const uint64_t tiles = (g.nblocks + tile - 1) / tile + 1;
   uint64_t cap = g.nblocks / 16 + 4096;
   if (cap > ((uint64_t)1 << 24)) cap = (uint64_t)1 << 24;
   uint16_t* lengths;
@@ -470,29 +459,8 @@ static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm,
   CU(cudaMemsetAsync(stat, 0, 16, st));
   EncodeArgs a = { d_data, g, prm, d_words, start_bit, 0, lengths, 0, g.nblocks, st, 1 };
   int rc;
-  bool handover = false;
-  if (probe) {
-    CU(cudaMemsetAsync(stat + 16, 0, ((probe + tile - 1) / tile) * 16, st));
-    a.b1 = probe;
-    if ((rc = launch_var1(type, a, v))) return rc;
-    unsigned int h[2];
-    CU(cudaMemcpyAsync(h, stat, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    handover = (uint64_t)h[1] * 16 > probe;
-    a.b0 = probe;
-    a.b1 = g.nblocks;
-  }
-  if (!handover) {
-    CU(cudaMemsetAsync(stat, 0, 4, st));  // tickets start over, the overflow count runs on
-    CU(cudaMemsetAsync(stat + 16, 0, ((a.b1 - a.b0 + tile - 1) / tile) * 16, st));
-    if ((rc = launch_var1(type, a, v))) return rc;
-  }
-  else {
-    uint64_t* cursor = reinterpret_cast<uint64_t*>(carry) + 4;  // (the slot path's cursor lives behind the carry)
-    carry_to_cursor<<<1, 1, 0, st>>>(carry, static_cast<uint64_t*>(d_words), cursor);
-    LAUNCHED();
-    *resume = probe;
-  }
+  CU(cudaMemsetAsync(stat + 16, 0, ((a.b1 - a.b0 + tile - 1) / tile) * 16, st));
+  if ((rc = launch_var1(type, a, v))) return rc;
   v.cleanup = 1;
   if ((rc = launch_var1(type, a, v))) return rc;
   if (index) {
@@ -501,8 +469,6 @@ static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm,
     index->key_start = start_bit;
     index->total_bits = 0;
   }
-  if (handover)
-    return ZFP_B200_OK;
   if (d_end_bit) {  // stream-ordered: the size stays on the device
     finish_async_var1<<<1, 1, 0, st>>>(d_end_bit, carry, v.overflow_count, v.overflow_capacity);
     LAUNCHED();
@@ -514,7 +480,7 @@ static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm,
   CU(cudaMemcpyAsync(h_cnt, stat, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   if (h_cnt[1] > cap) {
-    // more long blocks than the list holds (the probe saw few): start over on the slot path
+    // more long blocks than the list holds: start over on the slot path
     *resume = 0;
     return ZFP_B200_OK;
   }
@@ -593,12 +559,11 @@ static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words
   // shifted plain stores.  Bit-exact and without the slot scratch, but measured SLOWER than the slot path below on
   // the B200 (1024^3 fp64 accuracy 1e-6: 6.39 ms against 5.78 ms), so it is not the default.
   static const bool single_pass = getenv("ZFP_B200_VAR1") != nullptr;
-  uint64_t first_block = 0;
-  bool resumed = false;
-  if (dims == 3 && single_pass) {
-    rc = encode_var1(d, g, prm, d_data, d_words, start_bit, end_bit, d_end_bit, index, st, &first_block);
-    if (rc || first_block >= g.nblocks) return rc;
-    resumed = first_block != 0;  // the slot path continues where the single pass handed over (0: it starts over)
+  // (reversible mode on 64-bit types: nearly every block outgrows the window - straight to the slot path)
+  if (dims == 3 && single_pass && !(prm.minexp < kMinExp && (type == T_DOUBLE || type == T_INT64))) {
+    uint64_t resume = 0;
+    rc = encode_var1(d, g, prm, d_data, d_words, start_bit, end_bit, d_end_bit, index, st, &resume);
+    if (rc || resume >= g.nblocks) return rc;  // (otherwise: too many long blocks, start over below)
   }
 
   // variable rate: encode into per-block scratch slots, scan the lengths, compact bit-granularly
@@ -621,15 +586,11 @@ static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words
   uint64_t* offsets = static_cast<uint64_t*>(scratch(SCR_OFFSETS, chunk * 8));
   uint64_t* cursor = static_cast<uint64_t*>(scratch(SCR_CURSOR, 64));
   if (!lengths || !slots || !tiles || !offsets || !cursor) return ZFP_B200_ECUDA;
-  if (resumed)
-    cursor += 4;  // left there by carry_to_cursor, with the partial word already in place
-  else {
-    set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
-    LAUNCHED();
-    clear_word_tail<<<1, 1, 0, st>>>(static_cast<uint64_t*>(d_words), start_bit);
-    LAUNCHED();
-  }
-  for (uint64_t b0 = first_block; b0 < g.nblocks; b0 += chunk) {
+  set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
+  LAUNCHED();
+  clear_word_tail<<<1, 1, 0, st>>>(static_cast<uint64_t*>(d_words), start_bit);
+  LAUNCHED();
+  for (uint64_t b0 = 0; b0 < g.nblocks; b0 += chunk) {
     const uint64_t b1 = b0 + chunk < g.nblocks ? b0 + chunk : g.nblocks, cn = b1 - b0;
     rc = encode_any(2, type, dims, d_data, g, prm, slots, 0, slot_words, lengths, b0, b1, st);
     if (rc) return rc;

@@ -30,13 +30,14 @@
 
 #include "types.h"
 #include "zfp_perm_tables.h"
+#include "coder_luts.h"
 
 namespace zb {
 
-// developer switch for A/B timing: 0 removes the narrow (32-bit) plane steps of the 64-value coders
 #ifndef ZB_FP64_TAIL
 #define ZB_FP64_TAIL 1  // inverse transform of fp64 blocks on the FP64 pipe where that is exact (decode_block)
 #endif
+// developer switch for A/B timing: 0 removes the narrow (32-bit) plane steps of the 64-value coders
 #ifndef ZB_NARROW
 #define ZB_NARROW 0
 #endif
@@ -172,9 +173,12 @@ struct ColWriter {
   // single-pass variable rate (kernels_var1.cuh): no slot - a block that outgrows the window just counts
   // its bits (`drained` > 0 afterwards marks it) and is encoded again, in place, by the clean-up kernel
   bool sink;
+  // shared-space address of a copy of kEncLut8 (0: none): the small-universe plane steps, encode_planes_small8
+  uint32_t lut;
 
   __device__ __forceinline__ void init(uint32_t* column, uint32_t* slot = nullptr, uint32_t capacity_words = 0, bool count_only = false)
   {
+    lut = 0;
     base = (uint32_t)__cvta_generic_to_shared(column);
     acc = 0;
     bp = 0;
@@ -719,7 +723,7 @@ template <int H> __device__ __forceinline__ void set_half(uint64_t& u, uint32_t 
 // coded planes reach them).  Planes kup.. of the set are 32-bit work for the coder (narrow plane
 // steps), and with kup == 0 the words of coefficients 32..63 are not transposed at all.
 template <int H, int NEG, class UInt, int N>
-__device__ __forceinline__ int to_planes_half(const UInt (&u)[N], typename PlaneWord<N>::type* sp)
+__device__ __forceinline__ int to_planes_half(const UInt (&u)[N], typename PlaneWord<N>::type* sp, int* ksmall8 = nullptr)
 {
   if constexpr (N == 16 || N == 4) {
     uint32_t a[N];
@@ -745,6 +749,14 @@ __device__ __forceinline__ int to_planes_half(const UInt (&u)[N], typename Plane
       any_upper |= a1[i] ^ NegaWord<NEG>::w32;
     }
     const int kup = 32 - __clz((int)__reduce_or_sync(0xffffffffu, any_upper));
+    if (ksmall8) {
+      // planes >= *ksmall8 of the set have one-bits in coefficients 0..7 only, in every block of the warp
+      uint32_t any_mid = any_upper;
+#pragma unroll
+      for (int i = 8; i < 32; i++)
+        any_mid |= a0[i] ^ NegaWord<NEG>::w32;
+      *ksmall8 = 32 - __clz((int)__reduce_or_sync(0xffffffffu, any_mid));
+    }
     transpose32<NEG>(a0);
     if (kup == 0) {
 #pragma unroll
@@ -1101,6 +1113,41 @@ __device__ __forceinline__ bool encode_pair_narrow(ColWriter& bw, uint32_t limit
   done = d2;
   pos = p2.top;  // (a finished lane's pos is never looked at again)
   return true;
+}
+
+// Small-universe plane steps (blocks of 64 values, no plane coded yet): planes kbase + 31 down to kbase + ksmall
+// of the resident set have one-bits in coefficients 0..7 only, in every block of the warp, so a plane's whole
+// string is one look-up in kEncLut8 by (n, byte) and one append - no votes, no special cases.  The walk stops
+// early enough that no lane can exhaust its budget (17 bits per plane at most) or pass its precision limit;
+// the general steps take over at st.k (even).  A finished lane walks the table's idle row.
+template <int N>
+__device__ __forceinline__ void encode_planes_small8(ColWriter& bw, uint32_t limit, int kmin, int kbase, int ksmall, LockState& st,
+                                                     const typename PlaneWord<N>::type* sp)
+{
+  constexpr uint32_t FULL = 0xffffffffu;
+  const uint32_t room = st.done ? 0xffffffffu : limit - bw.tell();         // (tell() <= limit here: nothing coded yet)
+  const int nmax = (int)(__reduce_min_sync(FULL, room) / 17u);
+  int kstop = kbase + ksmall;
+  const int kprec = (int)__reduce_max_sync(FULL, st.done ? 0u : (uint32_t)kmin);
+  kstop = kstop > kprec ? kstop : kprec;
+  kstop = kstop > kbase ? kstop : kbase;
+  kstop = kstop > st.k - nmax ? kstop : st.k - nmax;
+  kstop = (kstop + 1) & ~1;
+  if (kstop >= st.k)
+    return;
+  const uint32_t planes = (uint32_t)__cvta_generic_to_shared(sp);
+  uint32_t row = bw.lut + (st.done ? 9u << 10 : 0u);  // byte address of the table row of n
+  int k = st.k;
+#pragma unroll 2
+  for (; k > kstop; k--) {
+    uint32_t b, e;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(planes + (uint32_t)(k - 1 - kbase) * 32u * (uint32_t)sizeof(typename PlaneWord<N>::type)));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(row + (b << 2)));
+    bw.append32(e & 0x1ffffu, (e >> 17) & 31u);
+    row = bw.lut + ((e >> 22) << 10);
+  }
+  st.k = kstop;
+  st.pos = st.done ? 0u : (row - bw.lut) >> 10;
 }
 
 // planes k-1 .. klo of the resident set (first plane kbase), two per vote (k and klo are even).
@@ -1805,7 +1852,11 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
       // undivided half, blocks that go a few planes further (rate 8) with a 16-plane window.
       if (st.k > 32) {
         stage_rendezvous<SYNC_THREADS>();
-        const int kup = to_planes_half<1, NEG, UInt, N>(u, sp);
+        int ksmall = 32;
+        const int kup = to_planes_half<1, NEG, UInt, N>(u, sp, (!REV && bw.lut) ? &ksmall : nullptr);
+        if constexpr (!REV)
+          if (bw.lut)
+            encode_planes_small8<N>(bw, limit, kmin, 32, ksmall, st, sp);
         encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp, 32 + kup);
       }
 #pragma unroll 1
@@ -1846,7 +1897,50 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
   return bits;
 }
 
-template <int TYPE, int DIMS, bool REV, class Reader>
+// Register budget of a warpgroup (PTX setmaxnreg; all four warps of the group execute it together)
+template <int REGS> __device__ __forceinline__ void wg_reg_release() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
+template <int REGS> __device__ __forceinline__ void wg_reg_acquire() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
+// the four warps of a warpgroup meet (named barrier 1 + group index)
+__device__ __forceinline__ void wg_barrier()
+{
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + (threadIdx.x >> 7)) : "memory");
+}
+
+// The large register budget goes to whole warpgroups: setmaxnreg allocates warp by warp, and warps of three groups
+// that each hold a part of the pool would wait for one another at their group barriers for ever.  A counter in
+// shared memory (set by the kernel to the number of groups the pool can make large) is taken by a group's first
+// thread before any of its warps asks for registers, so the hardware request never has to wait.
+__device__ __forceinline__ int* wg_large_slots()
+{
+  __shared__ int slots;
+  return &slots;
+}
+template <int REGS>
+__device__ __forceinline__ void wg_enter_large()
+{
+  wg_barrier();
+  if ((threadIdx.x & 127) == 0) {
+    int* slots = wg_large_slots();
+    while (atomicSub(slots, 1) <= 0) {
+      atomicAdd(slots, 1);
+      __nanosleep(200);
+    }
+  }
+  wg_barrier();
+  wg_reg_acquire<REGS>();
+}
+template <int REGS>
+__device__ __forceinline__ void wg_leave_large()
+{
+  wg_reg_release<REGS>();
+  wg_barrier();
+  if ((threadIdx.x & 127) == 0)
+    atomicAdd(wg_large_slots(), 1);
+}
+
+// PS > 0 (kernels_ps.cuh, blocks of 64 64-bit values): the caller's warpgroup holds a small register
+// budget while it parses planes 63..32 and acquires PS registers per thread before the first transposes.
+template <int TYPE, int DIMS, bool REV, class Reader, int PS = 0>
 __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (&v)[1 << (2 * DIMS)],
                                                  const Params& prm, Reader& br,
                                                  typename PlaneWord<(1 << (2 * DIMS))>::type* sp)
@@ -1895,9 +1989,11 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     const uint32_t budget = prm.maxbits - bits;
     const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
     LockDecodeState st = { budget, 0, P, P, zero };
+    if constexpr (!PS) {
 #pragma unroll
-    for (int i = 0; i < N; i++)
-      u[i] = (UInt)NegaWord<NEG>::w64;
+      for (int i = 0; i < N; i++)
+        u[i] = (UInt)NegaWord<NEG>::w64;
+    }
     if constexpr (REV) {
       // mirror of the encoder's shortcut: leading '0' tests while no coefficient is significant are
       // empty planes; the warp skips the ones all its blocks have in common (even count, at most the
@@ -1918,6 +2014,12 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     if constexpr (P == 64 && N == 64) {
       // (coefficients 32..63 are transposed only once some block of the warp has one of them significant)
       decode_planes_any<N>(br, kmin, 32, 32, st, sp);
+      if constexpr (PS) {
+        wg_enter_large<PS>();
+#pragma unroll
+        for (int i = 0; i < N; i++)
+          u[i] = (UInt)NegaWord<NEG>::w64;
+      }
       from_planes_half<1, NEG, UInt, N>(u, sp, st.lowest, __any_sync(0xffffffffu, st.n > 32));
       if (__any_sync(0xffffffffu, !st.done && st.k > kmin && st.bits != 0)) {
         decode_planes_any<N>(br, kmin, 16, 16, st, sp);
@@ -1927,7 +2029,11 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
           from_planes_window<0, NEG>(u, sp, st.lowest, __any_sync(0xffffffffu, st.n > 32));
         }
       }
-      __syncthreads();  // the warps of the CTA enter the long straight-line tail together (shared instruction fetch)
+      // the warps of the CTA (PS: of the warpgroup) enter the long straight-line tail together (shared instruction fetch)
+      if constexpr (PS)
+        wg_barrier();
+      else
+        __syncthreads();
     }
     else if constexpr (P == 64) {
       decode_planes_lockstep<N>(br, kmin, 32, 32, st, sp);

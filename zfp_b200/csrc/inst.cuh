@@ -9,6 +9,7 @@
 #include "kernels4d.cuh"
 #include "kernels4q.cuh"
 #include "kernels_ws.cuh"
+#include "kernels_ps.cuh"
 #include "kernels_q4.cuh"
 #include "kernels_var1.cuh"
 
@@ -51,6 +52,13 @@ inline cudaError_t allow_smem_cached(K kernel, size_t bytes, size_t (&granted)[6
 
 template <int TYPE> cudaError_t run_encode_q4(const EncodeArgs& a);
 
+// developer knob (occupancy experiments): extra dynamic shared memory per CTA of the staged kernels, bytes
+inline size_t smem_pad()
+{
+  static const size_t pad = getenv("ZFP_B200_SMEM_PAD") ? (size_t)atol(getenv("ZFP_B200_SMEM_PAD")) : 0;
+  return pad;
+}
+
 template <int TYPE, int DIMS, bool REV>
 cudaError_t run_encode_staged(const EncodeArgs& a)
 {
@@ -63,7 +71,8 @@ cudaError_t run_encode_staged(const EncodeArgs& a)
   auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
   constexpr int threads = EncCfg<TYPE>::threads;
   const size_t smem = (size_t)(threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
-                                                ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4);
+                                                ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4) +
+                      ((ZB_SMALL8 && N == 64 && Traits<TYPE>::P == 64 && !REV) ? kEncLut8Words * 4 : 0) + smem_pad();
   static size_t granted[64] = { 0 };  // per kernel instance
   cudaError_t e = allow_smem_cached(kernel, smem, granted);
   if (e != cudaSuccess) return e;
@@ -156,6 +165,24 @@ cudaError_t run_decode_ws(const DecodeArgs& a)
   return cudaGetLastError();
 }
 
+// phased register budget (kernels_ps.cuh): persistent CTAs, one per multiprocessor
+template <int TYPE>
+cudaError_t run_decode_ps(const DecodeArgs& a)
+{
+  auto kernel = decode_ps_kernel<TYPE>;
+  const size_t smem = ps_cta_bytes(a.prm.maxbits >> 5);
+  static size_t granted[64] = { 0 };
+  cudaError_t e = allow_smem_cached(kernel, smem, granted);
+  if (e != cudaSuccess) return e;
+  const uint64_t nbatches = (a.b1 - a.b0 + 127) / 128;
+  uint64_t ctas = (nbatches + kPsGroups - 1) / kPsGroups;
+  const uint64_t resident = (uint64_t)device_sms();
+  if (ctas > resident) ctas = resident;
+  kernel<<<(unsigned)ctas, kPsThreads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+                                                      static_cast<const uint64_t*>(a.in), a.start_bit, a.b0, a.b1);
+  return cudaGetLastError();
+}
+
 // four-lanes-per-block encoder (kernels_q4.cuh)
 template <int TYPE>
 cudaError_t run_encode_q4(const EncodeArgs& a)
@@ -194,13 +221,18 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
     static const bool q4 = getenv("ZFP_B200_Q4") != nullptr;
     if (q4 && !a.g.box && (kQ4Threads / 32) * q4_warp_bytes(a.prm.maxbits >> 5) <= 200 * 1024)
       return run_decode_q4<TYPE>(a);
+    static const bool ps = getenv("ZFP_B200_PS") != nullptr;
+    const uint32_t words = a.prm.maxbits >> 5;
+    if (ps && (words & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.in) + (a.start_bit >> 6) * 8) & 15) == 0 &&
+        ps_cta_bytes(words) <= 220 * 1024)
+      return run_decode_ps<TYPE>(a);
     static const bool ws = getenv("ZFP_B200_WS") != nullptr && ws_cta_bytes(4096 >> 5) > 0;
     if (ws && !a.g.box && ws_cta_bytes(a.prm.maxbits >> 5) <= 110 * 1024)
       return run_decode_ws<TYPE>(a);
   }
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
   const size_t smem = (size_t)(DecCfg<TYPE>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
-                                                 ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4);
+                                                 ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4) + smem_pad();
   static size_t granted[64] = { 0 };  // per kernel instance
   cudaError_t e = allow_smem_cached(kernel, smem, granted);
   if (e != cudaSuccess) return e;

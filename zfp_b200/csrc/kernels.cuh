@@ -108,6 +108,25 @@ __device__ __forceinline__ void pad4(T& a, T& b, T& c, T& d, uint32_t m)
   d = m < 4 ? a : d;
 }
 
+// L2 prefetch of the rows of a block another CTA will gather about one wave of CTAs later (full blocks with
+// contiguous rows only): the gather then waits for an L2 hit instead of HBM
+template <int DIMS, class Scalar>
+__device__ __forceinline__ void prefetch_block(const Scalar* data, const Geom& g, uint64_t b)
+{
+  constexpr int N = 1 << (2 * DIMS);
+  if (b >= g.nblocks || !g.vec_rows)
+    return;
+  const BlockPos<DIMS> pos = locate<DIMS>(g, b);
+  if (!pos.full)
+    return;
+  const Scalar* p = data + pos.offset;
+#pragma unroll
+  for (int r = 0; r < N / 4; r++) {
+    const int64_t o = (DIMS > 1 ? g.s[1] * (r & 3) : 0) + (DIMS > 2 ? g.s[2] * (r >> 2) : 0);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+  }
+}
+
 template <int DIMS, class Scalar>
 __device__ __forceinline__ void gather(Scalar (&v)[1 << (2 * DIMS)], const Scalar* data, const Geom& g,
                                        const BlockPos<DIMS>& pos)
@@ -221,12 +240,21 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_ENC64_THREADS
 #define ZB_ENC64_THREADS 128
 #endif
+// Two experiments on the staged encode of 64-bit 3-D blocks, both bit-exact, neither faster (1024^3 fp64 rate 8,
+// 4.31 ms without): an L2 prefetch of the rows another CTA gathers one wave later (4.57 ms), and table-driven
+// plane steps while only coefficients 0..7 are significant (encode_planes_small8: 11 % fewer instructions, 4.39 ms).
+#ifndef ZB_PREFETCH
+#define ZB_PREFETCH 0
+#endif
+#ifndef ZB_SMALL8
+#define ZB_SMALL8 0
+#endif
 #ifndef ZB_ENC_SYNC
 #define ZB_ENC_SYNC 0  // 1 with ZB_ENC64_THREADS = 256 / 384: warps on one scheduler rendezvous before the long stages
 #endif
 template <int TYPE> struct EncCfg {
   static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_ENC64_THREADS : kThreads;
-  static constexpr int min_ctas(bool rev)
+  __host__ __device__ static constexpr int min_ctas(bool rev)
   {
     // 64-bit: 384 threads per SM (<= 168 registers per thread), as with 6 CTAs of 64 threads
     return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? 6 : 9);
@@ -262,9 +290,25 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
   typename TR::Scalar v[N];
   gather<DIMS>(v, data, g, pos);
+#if ZB_PREFETCH
+  if constexpr (N == 64 && TR::P == 64) {
+    uint32_t nsm;
+    asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    constexpr int kWaveThreads = EncCfg<TYPE>::min_ctas(REV) * EncCfg<TYPE>::threads;  // per multiprocessor
+    prefetch_block<DIMS>(data, g, b_raw + (uint64_t)nsm * kWaveThreads);
+  }
+#endif
 
   ColWriter bw;
   bw.init(stage);
+  if constexpr (ZB_SMALL8 && N == 64 && TR::P == 64 && !REV) {
+    // the table of the small-universe plane steps (encode_planes_small8), one copy per CTA
+    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (EncCfg<TYPE>::threads / 32) * warp_bytes);  // (behind the warps' buffers)
+    for (int i = threadIdx.x; i < kEncLut8Words / 4; i += EncCfg<TYPE>::threads)
+      reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(kEncLut8) + i);
+    __syncthreads();
+    bw.lut = (uint32_t)__cvta_generic_to_shared(lut);
+  }
 #if ZB_ENC_SYNC
   encode_block<TYPE, DIMS, REV, ColWriter, (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) ? EncCfg<TYPE>::threads / 4 : 0>(v, prm, bw, sp);
 #else
