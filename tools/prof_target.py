@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import zfp_b200 as zb
 arg0 = sys.argv[1] if len(sys.argv) > 1 else "512"
-shape = tuple(int(v) for v in arg0.split("x")) if "x" in arg0 else (int(arg0),) * 3
+shape = tuple(int(v) for v in arg0.split("x") if v) if "x" in arg0 else (int(arg0),) * 3
 dtype = {"f64": torch.float64, "f32": torch.float32, "i32": torch.int32, "i64": torch.int64}[sys.argv[2] if len(sys.argv) > 2 else "f64"]
 arg = sys.argv[3] if len(sys.argv) > 3 else "8"
 mode = {"reversible": True} if arg == "rev" else {"accuracy": float(arg[1:])} if arg.startswith("a") else {"precision": int(arg[1:])} if arg.startswith("p") else {"rate": float(arg)}

@@ -1900,10 +1900,14 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
 // Register budget of a warpgroup (PTX setmaxnreg; all four warps of the group execute it together)
 template <int REGS> __device__ __forceinline__ void wg_reg_release() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS)); }
 template <int REGS> __device__ __forceinline__ void wg_reg_acquire() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS)); }
-// the four warps of a warpgroup meet (named barrier 1 + group index)
+// the warps of a group meet (named barrier 1 + group index); a group is one warpgroup or, with
+// ZB_PS_GROUP_THREADS = 256, two that change their budget together
+#ifndef ZB_PS_GROUP_THREADS
+#define ZB_PS_GROUP_THREADS 128
+#endif
 __device__ __forceinline__ void wg_barrier()
 {
-  asm volatile("bar.sync %0, 128;" ::"r"(1 + (threadIdx.x >> 7)) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + threadIdx.x / ZB_PS_GROUP_THREADS), "n"(ZB_PS_GROUP_THREADS) : "memory");
 }
 
 // The large register budget goes to whole warpgroups: setmaxnreg allocates warp by warp, and warps of three groups
@@ -1919,7 +1923,7 @@ template <int REGS>
 __device__ __forceinline__ void wg_enter_large()
 {
   wg_barrier();
-  if ((threadIdx.x & 127) == 0) {
+  if (threadIdx.x % ZB_PS_GROUP_THREADS == 0) {
     int* slots = wg_large_slots();
     while (atomicSub(slots, 1) <= 0) {
       atomicAdd(slots, 1);
@@ -1934,7 +1938,7 @@ __device__ __forceinline__ void wg_leave_large()
 {
   wg_reg_release<REGS>();
   wg_barrier();
-  if ((threadIdx.x & 127) == 0)
+  if (threadIdx.x % ZB_PS_GROUP_THREADS == 0)
     atomicAdd(wg_large_slots(), 1);
 }
 

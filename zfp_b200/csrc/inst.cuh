@@ -174,7 +174,7 @@ cudaError_t run_decode_ps(const DecodeArgs& a)
   static size_t granted[64] = { 0 };
   cudaError_t e = allow_smem_cached(kernel, smem, granted);
   if (e != cudaSuccess) return e;
-  const uint64_t nbatches = (a.b1 - a.b0 + 127) / 128;
+  const uint64_t nbatches = (a.b1 - a.b0 + kPsGroupThreads - 1) / kPsGroupThreads;
   uint64_t ctas = (nbatches + kPsGroups - 1) / kPsGroups;
   const uint64_t resident = (uint64_t)device_sms();
   if (ctas > resident) ctas = resident;

@@ -249,15 +249,21 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_SMALL8
 #define ZB_SMALL8 0
 #endif
+#ifndef ZB_ENC32_THREADS
+#define ZB_ENC32_THREADS kThreads
+#endif
+#ifndef ZB_DEC32_THREADS
+#define ZB_DEC32_THREADS kThreads
+#endif
 #ifndef ZB_ENC_SYNC
 #define ZB_ENC_SYNC 0  // 1 with ZB_ENC64_THREADS = 256 / 384: warps on one scheduler rendezvous before the long stages
 #endif
 template <int TYPE> struct EncCfg {
-  static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_ENC64_THREADS : kThreads;
+  static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_ENC64_THREADS : ZB_ENC32_THREADS;
   __host__ __device__ static constexpr int min_ctas(bool rev)
   {
     // 64-bit: 384 threads per SM (<= 168 registers per thread), as with 6 CTAs of 64 threads
-    return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? 6 : 9);
+    return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? 6 : 9) * 64 / threads;
   }
 };
 constexpr int kStageSlack = 10;   // words of overshoot room: a plane may exceed the budget by < 200 bits and an append stores two words ahead
@@ -350,8 +356,8 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 #define ZB_DEC64_THREADS 192
 #endif
 template <int TYPE> struct DecCfg {
-  static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_DEC64_THREADS : kThreads;
-  static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? 6 : 9); }
+  static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_DEC64_THREADS : ZB_DEC32_THREADS;
+  static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? 6 : 9) * 64 / ZB_DEC32_THREADS; }
 };
 constexpr int kReadSlack = 5;  // zero words after the block: a plane's reads reach 64 + 32 bits past the position, rounded up to words
 

@@ -21,7 +21,8 @@ namespace zb {
 #define ZB_PS_GROUPS 4
 #endif
 constexpr int kPsGroups = ZB_PS_GROUPS;
-constexpr int kPsThreads = kPsGroups * 128;
+constexpr int kPsGroupThreads = ZB_PS_GROUP_THREADS;  // 128, or 256: two warpgroups that move together
+constexpr int kPsThreads = kPsGroups * kPsGroupThreads;
 // registers per thread: the launch gives 65536 / threads (rounded down to 8); pool = groups x that
 //   4 groups: 128 at launch = 2 x 56 + 2 x 200;  5 groups: 96 at launch, 3 x 40 + 2 x 176 <= 480
 //   (the parse phase compiles to 33 registers)
@@ -31,7 +32,10 @@ constexpr int kPsThreads = kPsGroups * 128;
 #ifndef ZB_PS_BIG
 #define ZB_PS_BIG (ZB_PS_GROUPS == 4 ? 200 : 176)
 #endif
-constexpr int kPsLarge = 2;  // groups the pool can hold at kPsBig next to the others at kPsSmall
+#ifndef ZB_PS_LARGE
+#define ZB_PS_LARGE 2
+#endif
+constexpr int kPsLarge = ZB_PS_LARGE;  // groups the pool can hold at kPsBig next to the others at kPsSmall
 constexpr int kPsSmall = ZB_PS_SMALL;
 constexpr int kPsBig = ZB_PS_BIG;
 
@@ -56,12 +60,12 @@ decode_ps_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Param
   uint32_t stage_off = (threadIdx.x >> 5) * warp_bytes + kStagedPlanes * 32 * (uint32_t)sizeof(PW) + (threadIdx.x & 31) * 4u;
   asm volatile("" : "+r"(sp_off), "+r"(stage_off));
 
-  const uint64_t nbatches = (block1 - block0 + 127) >> 7;
+  const uint64_t nbatches = (block1 - block0 + kPsGroupThreads - 1) / kPsGroupThreads;
   wg_reg_release<kPsSmall>();
-  for (uint64_t batch = (uint64_t)blockIdx.x * kPsGroups + (threadIdx.x >> 7); batch < nbatches; batch += (uint64_t)gridDim.x * kPsGroups) {
+  for (uint64_t batch = (uint64_t)blockIdx.x * kPsGroups + threadIdx.x / kPsGroupThreads; batch < nbatches; batch += (uint64_t)gridDim.x * kPsGroups) {
     PW* sp = reinterpret_cast<PW*>(reinterpret_cast<char*>(smem_raw) + sp_off);
     uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + stage_off);
-    const uint64_t b_raw = block0 + (batch << 7) + (threadIdx.x & 127);
+    const uint64_t b_raw = block0 + batch * kPsGroupThreads + threadIdx.x % kPsGroupThreads;
     const bool valid = b_raw < block1;
     const uint64_t b_list = valid ? b_raw : block1 - 1;
     const uint64_t b = g.box ? box_block(g, b_list) : b_list;
