@@ -279,6 +279,25 @@ def test_foreign_variable_rate_stream_without_index(zb, port, ref):
             assert got.tobytes() == want.tobytes(), (shape, mode)
 
 
+def test_untrusted_block_index_cannot_mislead_the_decoder(zb, port):
+    """A block index that comes from outside (zfp_b200_index_import, the zfpy trailer) with lengths that
+    are wrong - every block at the 16-bit maximum, all zero, or those of another field - must neither
+    send reads past the stream (the scan and the staging cap every length at the worst case of a block)
+    nor change the result: the decode notices the mismatch and rebuilds the index from the stream."""
+    for dtype, shape in ((np.float64, (36, 40, 44)), (np.float32, (70, 66)), (np.int32, (20, 12, 9, 5))):
+        a = make_field(shape, dtype, seed=5, kind="smooth")
+        other = make_field(shape, dtype, seed=6, kind="noise")
+        nblocks = int(np.prod([(n + 3) // 4 for n in shape]))
+        for mode in ({"precision": 20}, {"reversible": True}):
+            words = port.compress(a, **mode)
+            want = port.decompress(words, a.shape, a.dtype, **mode)
+            _, _, foreign = zb.compress_numpy(other, want_index=True, **mode)
+            for lengths in (np.full(nblocks, 65535, np.uint16), np.zeros(nblocks, np.uint16), np.asarray(foreign, np.uint16)):
+                got, used = zb.decompress_numpy(words, a.shape, a.dtype, index=lengths, **mode)
+                assert used == words.nbytes, (shape, mode)
+                assert got.tobytes() == want.tobytes(), (shape, mode)
+
+
 def test_openmp_reference_stream_is_identical(zb, ref):
     """The reference guarantees policy-independent streams (docs/source/execution.rst:56-57): the
     GPU stream equals the serial AND the OpenMP reference streams."""

@@ -361,14 +361,14 @@ static int decode_any(int offs_mode, int type, uint32_t dims, void* data, const 
 
 // exclusive scan of `n` block lengths into bit offsets, continuing at cursor[1]
 static int scan_lengths(const uint16_t* lengths, uint64_t n, uint64_t* tiles, uint64_t* offsets, uint64_t* cursor,
-                        cudaStream_t st)
+                        cudaStream_t st, uint32_t cap = 0xffffffffu)
 {
   const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  scan_tile_sums<<<(unsigned)ntiles, kScanThreads, 0, st>>>(lengths, n, tiles);
+  scan_tile_sums<<<(unsigned)ntiles, kScanThreads, 0, st>>>(lengths, n, tiles, cap);
   LAUNCHED();
   scan_tile_offsets<<<1, 1024, 0, st>>>(tiles, ntiles, cursor);
   LAUNCHED();
-  scan_apply<<<(unsigned)ntiles, kScanThreads, 0, st>>>(lengths, n, tiles, offsets);
+  scan_apply<<<(unsigned)ntiles, kScanThreads, 0, st>>>(lengths, n, tiles, offsets, cap);
   LAUNCHED();
   return ZFP_B200_OK;
 }
@@ -736,7 +736,7 @@ static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_word
   if (!tiles || !offsets || !cursor) return ZFP_B200_ECUDA;
   set_cursor<<<1, 1, 0, st>>>(cursor, start_bit);
   LAUNCHED();
-  rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st);
+  rc = scan_lengths(lengths, g.nblocks, tiles, offsets, cursor, st, block_capacity_bits(d));
   if (rc) return rc;
   rc = decode_any(1, d->type, d->dims, d_data, g, prm, d_words, start_bit, offsets, lengths, st, block0, block1,
                   d_status ? d_status : reinterpret_cast<uint32_t*>(cursor + 2));

@@ -498,7 +498,13 @@ decode_var_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Para
   const uint64_t b_list = valid ? b_raw : block1 - 1;
   const uint64_t b = g.box ? box_block(g, b_list) : b_list;
   const uint64_t off = offsets[b];
-  const uint32_t phase = (uint32_t)(off & 31), len = lengths[b];
+  // (an indexed length beyond the worst case of a block - the per-block term of zfp_stream_maximum_size,
+  // src/zfp.c:711-742, as in the scan - is not believed: the staging below never reads past that)
+  constexpr uint32_t header = TR::is_fp ? (REV ? 2 + TR::EBITS + TR::PBITS : 1 + TR::EBITS) : (REV ? TR::PBITS : 0);
+  uint32_t cap = header + N - 1 + N * (prm.maxprec < (uint32_t)TR::P ? prm.maxprec : (uint32_t)TR::P);
+  cap = cap > prm.maxbits ? prm.maxbits : cap;
+  cap = cap < prm.minbits ? prm.minbits : cap;
+  const uint32_t phase = (uint32_t)(off & 31), len = min((uint32_t)lengths[b], cap);
   ColReader br;
   br.init_var(stage, kVarStageWords, in + (off >> 5), (phase + len + 31) >> 5, phase);
   br.set_run_table(run_table);

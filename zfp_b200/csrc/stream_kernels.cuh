@@ -43,13 +43,15 @@ __device__ __forceinline__ uint64_t cta_excl_scan64(uint64_t v, uint64_t& total)
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_tile_sums(const uint16_t* __restrict__ lengths, uint64_t n, uint64_t* __restrict__ tile_sum)
+scan_tile_sums(const uint16_t* __restrict__ lengths, uint64_t n, uint64_t* __restrict__ tile_sum, uint32_t cap)
 {
+  // (cap: no block is longer than the worst case the buffer was sized for - an index that came from outside,
+  // zfp_b200_index_import, cannot steer the decoder past the stream; the decode then reports the mismatch)
   const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
   uint32_t s = 0;
 #pragma unroll
   for (int i = 0; i < kScanPerThread; i++)
-    s += base + i < n ? lengths[base + i] : 0u;
+    s += base + i < n ? min((uint32_t)lengths[base + i], cap) : 0u;
   uint32_t total;
   cta_excl_scan(s, total);
   if (threadIdx.x == 0)
@@ -79,13 +81,13 @@ scan_tile_offsets(uint64_t* __restrict__ tile_sum, uint64_t ntiles, uint64_t* __
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_apply(const uint16_t* __restrict__ lengths, uint64_t n, const uint64_t* __restrict__ tile_off,
-           uint64_t* __restrict__ offsets)
+           uint64_t* __restrict__ offsets, uint32_t cap)
 {
   const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPerThread;
   uint32_t len[kScanPerThread], s = 0;
 #pragma unroll
   for (int i = 0; i < kScanPerThread; i++) {
-    len[i] = base + i < n ? lengths[base + i] : 0u;
+    len[i] = base + i < n ? min((uint32_t)lengths[base + i], cap) : 0u;
     s += len[i];
   }
   uint32_t total;
