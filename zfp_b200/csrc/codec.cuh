@@ -990,6 +990,17 @@ __device__ __forceinline__ void encode_plane_lockstep(ColWriter& bw, uint32_t li
   constexpr uint32_t FULL = 0xffffffffu;
   bw.drain_if_low();
   done = done || k < kmin || bw.tell() >= limit;
+  if constexpr (N == 4) {
+    // blocks of four values: the plane's whole string by table (kEncLut4, every plane word and every n: no
+    // special cases, no votes); a finished lane walks the idle row (empty string)
+    if (bw.lut) {
+      uint32_t e;
+      asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(bw.lut + ((done ? 5u : pos) << 6) + ((uint32_t)x << 2)));
+      bw.append32(e & 0xffu, (e >> 8) & 15u);
+      pos = e >> 12;
+      return;
+    }
+  }
   const uint32_t n = done ? 0u : pos;  // a finished lane appends nothing: zero-length verbatim part, empty T
   R r, verb;
   if constexpr (N > 32) {

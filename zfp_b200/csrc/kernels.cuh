@@ -307,6 +307,14 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 
   ColWriter bw;
   bw.init(stage);
+  if constexpr (N == 4) {
+    // the plane-string table of the 4-value blocks (kEncLut4), one copy per CTA behind the warps' buffers
+    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (EncCfg<TYPE>::threads / 32) * warp_bytes);
+    for (int i = threadIdx.x; i < kEncLut4Words; i += EncCfg<TYPE>::threads)
+      lut[i] = kEncLut4[i];
+    __syncthreads();
+    bw.lut = (uint32_t)__cvta_generic_to_shared(lut);
+  }
   if constexpr (ZB_SMALL8 && N == 64 && TR::P == 64 && !REV) {
     // the table of the small-universe plane steps (encode_planes_small8), one copy per CTA
     uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (EncCfg<TYPE>::threads / 32) * warp_bytes);  // (behind the warps' buffers)
