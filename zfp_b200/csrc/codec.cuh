@@ -730,6 +730,15 @@ __device__ __forceinline__ int to_planes_half(const UInt (&u)[N], typename Plane
 #pragma unroll
     for (int i = 0; i < N; i++)
       a[i] = (uint32_t)(u[i] >> (32 * H));
+    if constexpr (N == 16) {
+      if (ksmall8) {
+        uint32_t any_upper = 0;
+#pragma unroll
+        for (int i = 8; i < 16; i++)
+          any_upper |= a[i] ^ NegaWord<NEG>::w32;
+        *ksmall8 = 32 - __clz((int)__reduce_or_sync(0xffffffffu, any_upper));
+      }
+    }
     transpose_small<N, NEG>(a);
 #pragma unroll
     for (int q = 0; q < 32 / N; q++)
@@ -1126,39 +1135,39 @@ __device__ __forceinline__ bool encode_pair_narrow(ColWriter& bw, uint32_t limit
   return true;
 }
 
-// Small-universe plane steps (blocks of 64 values, no plane coded yet): planes kbase + 31 down to kbase + ksmall
-// of the resident set have one-bits in coefficients 0..7 only, in every block of the warp, so a plane's whole
-// string is one look-up in kEncLut8 by (n, byte) and one append - no votes, no special cases.  The walk stops
-// early enough that no lane can exhaust its budget (17 bits per plane at most) or pass its precision limit;
-// the general steps take over at st.k (even).  A finished lane walks the table's idle row.
+// Small-universe plane steps (blocks of 16 or 64 values, at most 8 coefficients significant so far): planes
+// kbase + 31 down to kbase + ksmall of the resident set have one-bits in coefficients 0..7 only, in every block
+// of the warp, so a plane's whole string is one look-up in kEncLut8 by (n, byte) and one append - no special
+// cases, and one vote per two planes: the walk stops while every lane still has room for two strings of 17 bits,
+// and at the highest precision limit of the warp; the general steps take over at st.k (even).  A finished lane
+// walks the table's idle row.
 template <int N>
 __device__ __forceinline__ void encode_planes_small8(ColWriter& bw, uint32_t limit, int kmin, int kbase, int ksmall, LockState& st,
                                                      const typename PlaneWord<N>::type* sp)
 {
   constexpr uint32_t FULL = 0xffffffffu;
-  const uint32_t room = st.done ? 0xffffffffu : limit - bw.tell();         // (tell() <= limit here: nothing coded yet)
-  const int nmax = (int)(__reduce_min_sync(FULL, room) / 17u);
   int kstop = kbase + ksmall;
   const int kprec = (int)__reduce_max_sync(FULL, st.done ? 0u : (uint32_t)kmin);
   kstop = kstop > kprec ? kstop : kprec;
   kstop = kstop > kbase ? kstop : kbase;
-  kstop = kstop > st.k - nmax ? kstop : st.k - nmax;
   kstop = (kstop + 1) & ~1;
-  if (kstop >= st.k)
-    return;
   const uint32_t planes = (uint32_t)__cvta_generic_to_shared(sp);
-  uint32_t row = bw.lut + (st.done ? 9u << 10 : 0u);  // byte address of the table row of n
+  uint32_t row = bw.lut + ((st.done ? 9u : st.pos) << 10);  // byte address of the table row of n
   int k = st.k;
-#pragma unroll 2
-  for (; k > kstop; k--) {
-    uint32_t b, e;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(planes + (uint32_t)(k - 1 - kbase) * 32u * (uint32_t)sizeof(typename PlaneWord<N>::type)));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(row + (b << 2)));
-    bw.append32(e & 0x1ffffu, (e >> 17) & 31u);
-    row = bw.lut + ((e >> 22) << 10);
+  for (; k > kstop; k -= 2) {
+    if (__any_sync(FULL, !st.done && limit - bw.tell() < 34u))  // (tell() <= limit: the walk never exhausts a budget)
+      break;
+#pragma unroll
+    for (int j = 1; j <= 2; j++) {
+      uint32_t b, e;
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(planes + (uint32_t)(k - j - kbase) * 32u * (uint32_t)sizeof(typename PlaneWord<N>::type)));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(row + (b << 2)));
+      bw.append32(e & 0x1ffffu, (e >> 17) & 31u);
+      row = bw.lut + ((e >> 22) << 10);
+    }
   }
-  st.k = kstop;
-  st.pos = st.done ? 0u : (row - bw.lut) >> 10;
+  st.pos = st.done ? st.pos : (row - bw.lut) >> 10;
+  st.k = k;
 }
 
 // planes k-1 .. klo of the resident set (first plane kbase), two per vote (k and klo are even).
@@ -1882,7 +1891,11 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     }
     else if constexpr (P == 64) {
       if (st.k > 32) {
-        const int kup = to_planes_half<1, NEG, UInt, N>(u, sp);
+        int ksmall = 32;
+        const int kup = to_planes_half<1, NEG, UInt, N>(u, sp, (N == 16 && !REV && bw.lut) ? &ksmall : nullptr);
+        if constexpr (N == 16 && !REV)
+          if (bw.lut)
+            encode_planes_small8<N>(bw, limit, kmin, 32, ksmall, st, sp);
         encode_planes_lockstep<N>(bw, limit, kmin, 32, 32, st, sp, 32 + kup);
       }
       if (__any_sync(0xffffffffu, !st.done && st.k > kmin && bw.tell() < limit)) {
@@ -1891,7 +1904,11 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
       }
     }
     else {
-      const int kup = to_planes_half<0, NEG, UInt, N>(u, sp);
+      int ksmall = 32;
+      const int kup = to_planes_half<0, NEG, UInt, N>(u, sp, (N == 16 && !REV && bw.lut) ? &ksmall : nullptr);
+      if constexpr (N == 16 && !REV)
+        if (bw.lut)
+          encode_planes_small8<N>(bw, limit, kmin, 0, ksmall, st, sp);
       encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp, kup);
     }
     const uint32_t used = bw.tell() - start;

@@ -315,7 +315,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
     __syncthreads();
     bw.lut = (uint32_t)__cvta_generic_to_shared(lut);
   }
-  if constexpr (ZB_SMALL8 && N == 64 && TR::P == 64 && !REV) {
+  if constexpr ((ZB_SMALL8 && N == 64 && TR::P == 64 && !REV) || (N == 16 && !REV)) {
     // the table of the small-universe plane steps (encode_planes_small8), one copy per CTA
     uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (EncCfg<TYPE>::threads / 32) * warp_bytes);  // (behind the warps' buffers)
     for (int i = threadIdx.x; i < kEncLut8Words / 4; i += EncCfg<TYPE>::threads)
