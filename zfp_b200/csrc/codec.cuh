@@ -326,6 +326,8 @@ struct ColReader {
   // shared-space address of the 32-entry table of test-bit positions used by the run decoder
   // (decode_planes_events): entry n has bits n, 2n+1, 3n+2, ... below 32 set
   uint32_t pm;
+  // shared-space address of a copy of kDecLut8h (0: none): the small-universe plane steps, decode_pair_small8
+  uint32_t lut8;
 
   __device__ __forceinline__ void init(const uint32_t* column)
   {
@@ -334,6 +336,7 @@ struct ColReader {
     gsrc = nullptr;
     left = cap = 0;
     pm = 0;
+    lut8 = 0;
   }
   __device__ __forceinline__ void set_run_table(const uint32_t* table) { pm = (uint32_t)__cvta_generic_to_shared(table); }
   // fill the table (one thread per entry; the caller synchronises the CTA afterwards)
@@ -364,6 +367,7 @@ struct ColReader {
     gsrc = src;
     left = words;
     pm = 0;
+    lut8 = 0;
     stage();
     bp = phase;
   }
@@ -1459,6 +1463,54 @@ __device__ __forceinline__ bool decode_pair_narrow(ColReader& br, int kmin, int 
   return true;
 }
 
+// Small-universe plane steps (blocks of 16 or 64 values), two planes per call: the mirror of encode_planes_small8.
+// While at most 8 coefficients are significant and a plane's group-tested part ends within nine bits without
+// reaching beyond coefficient 7, the part is ONE look-up in kDecLut8h by (n, the nine bits after the n verbatim
+// bits): bits consumed, one-bits deposited, n afterwards.  The second plane is parsed from the first one's
+// tentative state and ONE vote covers both: false - nothing stored, no state changed - when some lane needs the
+// general step (entry 0 of the table, n > 8, or fewer than n + 9 bits of budget left).
+struct Small8Parse {
+  uint32_t x, bits, bp, n;
+  bool ok;
+};
+__device__ __forceinline__ Small8Parse small8_plane_parse(const ColReader& br, bool dn, uint32_t bits, uint32_t bp, uint32_t n)
+{
+  Small8Parse r;
+  const uint32_t w = br.peek32(bp);
+  const uint32_t nn = n < 8 ? n : 8;                       // (n > 8: not ok, whatever is looked up)
+  const uint32_t t = shr32c(w, nn) & 511u;
+  uint32_t e;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(br.lut8 + (((nn << 9) + t) << 1)));
+  r.ok = dn || (n <= 8 && bits >= n + 9 && e != 0);
+  const uint32_t used = dn ? 0u : n + (e & 15u);
+  r.x = (w & mask32(n)) | ((e >> 4) & 0xffu);
+  r.n = dn ? n : e >> 12;
+  r.bits = bits - used;
+  r.bp = bp + used;
+  return r;
+}
+template <int N>
+__device__ __forceinline__ bool decode_pair_small8(ColReader& br, int kmin, int k, uint32_t& bits, uint32_t& n, int& lowest,
+                                                   bool& done, typename PlaneWord<N>::type* plane1, typename PlaneWord<N>::type* plane2)
+{
+  const bool dn1 = done || k - 1 < kmin || bits == 0;
+  const Small8Parse p1 = small8_plane_parse(br, dn1, bits, br.bp, n);
+  const bool dn2 = dn1 || k - 2 < kmin || p1.bits == 0;
+  const Small8Parse p2 = small8_plane_parse(br, dn2, p1.bits, p1.bp, p1.n);
+  if (__any_sync(0xffffffffu, !(p1.ok && p2.ok)))
+    return false;
+  if (!dn1)
+    *plane1 = (typename PlaneWord<N>::type)p1.x;
+  if (!dn2)
+    *plane2 = (typename PlaneWord<N>::type)p2.x;
+  done = dn2;
+  lowest = dn2 ? (dn1 ? lowest : k - 1) : k - 2;
+  bits = p2.bits;
+  br.bp = p2.bp;
+  n = p2.n;
+  return true;
+}
+
 template <int N>
 __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, int klo, int kbase, LockDecodeState& st,
                                                        typename PlaneWord<N>::type* sp)
@@ -1471,11 +1523,26 @@ __device__ __forceinline__ void decode_planes_lockstep(ColReader& br, int kmin, 
   // blocks of 64 values: narrow steps while no block of the warp has more than 32 significant coefficients
   // (n only grows, so once a pair has gone the general way with n > 32 somewhere the test is skipped)
   bool narrow = N > 32 && ZB_NARROW;
+  // small-universe steps until some block of the warp has more than 8 significant coefficients
+  bool small8 = (N == 16 || N == 64) && br.lut8 != 0 && !__any_sync(FULL, !done && n > 8);
   while (k > klo && __any_sync(FULL, !done)) {
     if (br.needs_restage()) {  // variable rate, long blocks: slide the window (positions in rec would go stale)
       finish_plane<N>(br, rec);
       rec.store = false;
       br.restage();
+    }
+    if constexpr (N == 16 || N == 64) {
+      if (small8) {
+        if constexpr (N > 32) {  // (a general step may have left its verbatim bits for later)
+          finish_plane<N>(br, rec);
+          rec.store = false;
+        }
+        if (decode_pair_small8<N>(br, kmin, k, bits, n, lowest, done, sp + (k - 1 - kbase) * 32, sp + (k - 2 - kbase) * 32)) {
+          k -= 2;
+          continue;
+        }
+        small8 = !__any_sync(FULL, !done && n > 8);
+      }
     }
     if constexpr (N > 32 && ZB_NARROW) {
       if (narrow) {

@@ -233,7 +233,8 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
   }
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
   const size_t smem = (size_t)(DecCfg<TYPE>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
-                                                 ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4) + smem_pad();
+                                                 ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4) +
+                      (kDecSmall8<N, REV> ? kDecLut8hBytes : 0) + smem_pad();
   static size_t granted[64] = { 0 };  // per kernel instance
   cudaError_t e = allow_smem_cached(kernel, smem, granted);
   if (e != cudaSuccess) return e;

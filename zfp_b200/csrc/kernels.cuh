@@ -367,6 +367,12 @@ template <int TYPE> struct DecCfg {
   static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_DEC64_THREADS : ZB_DEC32_THREADS;
   static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? 6 : 9) * 64 / ZB_DEC32_THREADS; }
 };
+// table-driven plane steps while only coefficients 0..7 are significant (decode_pair_small8): 2-D blocks;
+// 3-D blocks with -DZB_DSMALL8_3D=1 (experiment)
+#ifndef ZB_DSMALL8_3D
+#define ZB_DSMALL8_3D 0
+#endif
+template <int N, bool REV> constexpr bool kDecSmall8 = !REV && (N == 16 || (ZB_DSMALL8_3D && N == 64));
 constexpr int kReadSlack = 5;  // zero words after the block: a plane's reads reach 64 + 32 bits past the position, rounded up to words
 
 template <int TYPE, int DIMS, bool REV>
@@ -428,6 +434,14 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   ColReader br;
   br.init(stage);
   br.set_run_table(run_table);
+  if constexpr (kDecSmall8<N, REV>) {
+    // the table of the small-universe plane steps (decode_pair_small8), one copy per CTA behind the warps' buffers
+    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (DecCfg<TYPE>::threads / 32) * warp_bytes);
+    for (int i = threadIdx.x; i < kDecLut8hBytes / 16; i += DecCfg<TYPE>::threads)
+      reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(kDecLut8h) + i);
+    __syncthreads();
+    br.lut8 = (uint32_t)__cvta_generic_to_shared(lut);
+  }
   typename TR::Scalar v[N];
   decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
   if (valid) {
