@@ -249,6 +249,9 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_SMALL8
 #define ZB_SMALL8 0
 #endif
+#ifndef ZB_REV32_CTAS
+#define ZB_REV32_CTAS 6  // CTAs of 64 threads per SM the reversible 32-bit kernels are compiled for (register cap 170)
+#endif
 #ifndef ZB_ENC32_THREADS
 #define ZB_ENC32_THREADS kThreads
 #endif
@@ -263,7 +266,7 @@ template <int TYPE> struct EncCfg {
   __host__ __device__ static constexpr int min_ctas(bool rev)
   {
     // 64-bit: 384 threads per SM (<= 168 registers per thread), as with 6 CTAs of 64 threads
-    return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? 6 : 9) * 64 / threads;
+    return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? ZB_REV32_CTAS : 9) * 64 / threads;
   }
 };
 constexpr int kStageSlack = 10;   // words of overshoot room: a plane may exceed the budget by < 200 bits and an append stores two words ahead
@@ -365,7 +368,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 #endif
 template <int TYPE> struct DecCfg {
   static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_DEC64_THREADS : ZB_DEC32_THREADS;
-  static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? 6 : 9) * 64 / ZB_DEC32_THREADS; }
+  static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? ZB_REV32_CTAS : 9) * 64 / ZB_DEC32_THREADS; }
 };
 // table-driven plane steps while only coefficients 0..7 are significant (decode_pair_small8): 2-D blocks;
 // 3-D blocks with -DZB_DSMALL8_3D=1 (experiment)
