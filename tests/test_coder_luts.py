@@ -120,6 +120,20 @@ def test_decoder_table_agrees_with_the_reference_loop():
     assert 0 < escapes < 9 * 512 // 2
 
 
+def test_four_value_decoder_table_with_every_budget():
+    t = tables()["kDecLut4"]
+    for a in range(8):
+        for n in range(5):
+            for w in range(1 << a):
+                e = t[5 * ((1 << a) - 1) + (n << a) + w]
+                for tail in (0, 1):                                          # bits beyond the budget are never looked at
+                    stream = [0] * n + [(w >> i) & 1 for i in range(a)] + [tail] * 20
+                    budgets = (n + a,) if a < 7 else (n + 7, n + 9, n + 40)  # seven bits always suffice
+                    for budget in budgets:
+                        x, n2, used = ref_decode_plane(stream, n, 4, budget)
+                        assert (e & 15, (e >> 4) & 15, e >> 8) == (used - n, x, n2), (a, n, w, tail, budget)
+
+
 def test_committed_header_is_what_the_generator_writes(tmp_path):
     spec = importlib.util.spec_from_file_location("gen_coder_luts", os.path.join(ROOT, "tools", "gen_coder_luts.py"))
     gen = importlib.util.module_from_spec(spec)

@@ -19,6 +19,8 @@ bit "any one-bit left?", and after a '1' the remaining bits up to and including 
       bits 12..15  n after the plane
       bit  31      escape: the part does not end within nine bits, or reaches beyond coefficient 7
   kDecLut8h: the same in 16 bits (consumed | deposited << 4 | n after << 12; 0 = escape)
+  kDecLut4[5 * (2^a - 1) + (n << a) + t]  blocks of FOUR values, a = min(bits of budget left, 7), t = the next a bits:
+      consumed | deposited << 4 | n after << 8 (exact for every plane, budget end included)
 """
 import os
 
@@ -61,6 +63,38 @@ def enc4_entry(n, nibble):
     assert pos <= 4 and len(bits) <= 8
     s = sum(b << i for i, b in enumerate(bits))
     return s | (len(bits) << 8) | (pos << 12)
+
+
+def dec4_table():
+    """blocks of 4 values, the group-tested part of a plane under a bit budget (decode.c:96-117): entry
+    5 * (2^a - 1) + (n << a) + t for a = min(budget, 7) available bits t (first bit in bit 0), n = 0..4:
+    bits consumed | deposited one-bits << 4 | n after << 8.  Seven bits always suffice for four coefficients."""
+    tab = []
+    for a in range(8):
+        for n in range(5):
+            for t in range(1 << a):
+                bits, used, x, pos = a, 0, 0, n
+                def read():
+                    nonlocal used
+                    b = (t >> used) & 1
+                    used += 1
+                    return b
+                while bits and pos < 4:
+                    bits -= 1
+                    if read():
+                        while bits and pos < 3:
+                            bits -= 1
+                            if read():
+                                break
+                            pos += 1
+                        x |= 1 << pos
+                        pos += 1
+                    else:
+                        break
+                assert used <= 7 and (a < 7 or bits >= 0)
+                tab.append(used | (x << 4) | (pos << 8))
+    assert len(tab) == 5 * 255
+    return tab
 
 
 def dec_entry(n, t):
@@ -121,11 +155,13 @@ def main():
         # the decoder's table in 16 bits: consumed (0 = escape) | deposited bits << 4 | n after << 12
         dech = [0 if d >> 31 else (d & 15) | (((d >> 4) & 0xFF) << 4) | (((d >> 12) & 15) << 12) for d in dec]
         assert all(0 <= v < 65536 for v in dech) and all((v & 15) != 0 or d >> 31 for v, d in zip(dech, dec))
-        f.write("static __device__ __align__(16) const uint16_t kDecLut8h[%d] = {\n" % len(dech))
-        for i in range(0, len(dech), 12):
-            f.write("  " + ", ".join("0x%04x" % v for v in dech[i:i + 12]) + ",\n")
-        f.write("};\n\n")
-        f.write("constexpr int kEncLut8Words = %d;\nconstexpr int kDecLut8Words = %d;\nconstexpr int kEncLut4Words = %d;\nconstexpr int kDecLut8hBytes = %d;\n\n}  // namespace zb\n" % (len(enc), len(dec), len(enc4), 2 * len(dec)))
+        dec4 = dec4_table() + [0] * 5                                       # (padded to whole 16-byte groups)
+        for name, tab in (("kDecLut8h", dech), ("kDecLut4", dec4)):
+            f.write("static __device__ __align__(16) const uint16_t %s[%d] = {\n" % (name, len(tab)))
+            for i in range(0, len(tab), 12):
+                f.write("  " + ", ".join("0x%04x" % v for v in tab[i:i + 12]) + ",\n")
+            f.write("};\n\n")
+        f.write("constexpr int kEncLut8Words = %d;\nconstexpr int kDecLut8Words = %d;\nconstexpr int kEncLut4Words = %d;\nconstexpr int kDecLut8hBytes = %d;\nconstexpr int kDecLut4Bytes = %d;\n\n}  // namespace zb\n" % (len(enc), len(dec), len(enc4), 2 * len(dec), 2 * len(dec4)))
     print("wrote", OUT, len(enc), len(dec))
 
 

@@ -268,6 +268,7 @@ struct BitReader {
   const uint64_t* w;  // next word to fetch
   uint64_t buf;       // unread bits, LSB first
   uint32_t avail;     // number of valid bits in buf (0..64)
+  uint32_t lut4 = 0;  // shared-space address of a copy of kDecLut4 (0: none), blocks of four values (decode_planes)
 
   __device__ __forceinline__ void init(const void* words, uint64_t bitpos)
   {
@@ -1242,6 +1243,39 @@ __device__ __forceinline__ uint32_t decode_planes(BitReader& br, uint32_t budget
   return budget - bits;
 }
 
+// Blocks of four values with the table (br.lut4): the planes are not stored and transposed afterwards (64 plane
+// words and two 32 x 32 transposes for at most 4 x 64 bits) - each decoded plane's four bits go straight into the
+// four coefficients.  Returns the bits consumed; u = coefficients ^ NegaWord<NEG> like from_planes<NEG>.
+template <int P, int NEG, class UInt>
+__device__ __forceinline__ uint32_t decode_planes4_direct(BitReader& br, uint32_t budget, uint32_t maxprec, UInt (&u)[4])
+{
+  const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
+  uint32_t bits = budget, n = 0;
+  UInt c0 = 0, c1 = 0, c2 = 0, c3 = 0, kbit = (UInt)1 << (P - 1);
+  for (int k = P - 1; bits && k >= kmin; k--, kbit >>= 1) {
+    const uint32_t m = n < bits ? n : bits, left = bits - m, a = left < 7 ? left : 7;
+    const uint32_t w = (uint32_t)br.peek(m + a);
+    const uint32_t ones = (1u << a) - 1;
+    uint32_t e;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(br.lut4 + ((5u * ones + (n << a) + ((w >> m) & ones)) << 1)));
+    const uint32_t used = m + (e & 15u);
+    br.skip(used);
+    bits -= used;
+    n = e >> 8;
+    const uint32_t x = (w & ((1u << m) - 1)) | ((e >> 4) & 15u);
+    c0 |= (x & 1u) ? kbit : (UInt)0;
+    c1 |= (x & 2u) ? kbit : (UInt)0;
+    c2 |= (x & 4u) ? kbit : (UInt)0;
+    c3 |= (x & 8u) ? kbit : (UInt)0;
+  }
+  constexpr UInt mask = (UInt)NegaWord<NEG>::w64;
+  u[0] = c0 ^ mask;
+  u[1] = c1 ^ mask;
+  u[2] = c2 ^ mask;
+  u[3] = c3 ^ mask;
+  return budget - bits;
+}
+
 // Plane-lockstep decoder for the column reader, the mirror image of encode_planes_lockstep.  Per
 // plane a lane reads its m = min(n, bits) verbatim bits in one go, then parses the whole
 // group-tested part T from one 32-bit look at the stream without a loop over its items: with a
@@ -2151,9 +2185,18 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     lowest = st.lowest;
   }
   else if (!zero) {
-    int kstop;
-    bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
-    from_planes<NEG, UInt, N>(u, sp, kstop);
+    bool direct = false;
+    if constexpr (N == 4 && !is_lockstep<Reader>::value) {
+      if (br.lut4) {
+        bits += decode_planes4_direct<P, NEG>(br, prm.maxbits - bits, maxprec, u);
+        direct = true;
+      }
+    }
+    if (!direct) {
+      int kstop;
+      bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
+      from_planes<NEG, UInt, N>(u, sp, kstop);
+    }
   }
   else {
 #pragma unroll

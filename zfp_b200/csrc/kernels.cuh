@@ -556,6 +556,15 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   using PW = typename PlaneWord<N>::type;
   extern __shared__ uint64_t smem_raw[];
   PW* sp = reinterpret_cast<PW*>(smem_raw) + (threadIdx.x >> 5) * (TR::P * 32) + (threadIdx.x & 31);
+  uint32_t lut4 = 0;
+  if constexpr (N == 4) {
+    // the decoder table of the 4-value blocks (kDecLut4), one copy per CTA behind the plane buffers
+    uint4* lut = reinterpret_cast<uint4*>(reinterpret_cast<PW*>(smem_raw) + (kThreads / 32) * (TR::P * 32));
+    for (int i = threadIdx.x; i < kDecLut4Bytes / 16; i += kThreads)
+      lut[i] = __ldg(reinterpret_cast<const uint4*>(kDecLut4) + i);
+    __syncthreads();
+    lut4 = (uint32_t)__cvta_generic_to_shared(lut);
+  }
 
   const uint64_t b_list = block0 + (uint64_t)blockIdx.x * kThreads + threadIdx.x;
   if (b_list >= block1)
@@ -563,6 +572,7 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   const uint64_t b = g.box ? box_block(g, b_list) : b_list;
   BitReader br;
   br.init(in, OFFS ? offsets[b] : start_bit + b * (uint64_t)prm.maxbits);
+  br.lut4 = lut4;
   typename TR::Scalar v[N];
   const uint32_t bits = decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
   if (OFFS == 1 && check && lengths && bits != lengths[b])
