@@ -312,6 +312,31 @@ struct BitReader {
   }
 };
 
+// A block of at most 64 bits held in a register pair (1-D blocks at up to 16 bits per value): no refills.
+struct SmallReader {
+  static constexpr bool kStaged = false;
+  uint64_t buf;       // unread bits, LSB first; zero beyond the block
+  uint32_t lut4 = 0;  // as in BitReader
+
+  __device__ __forceinline__ void init(const void* words, uint64_t bitpos, uint32_t nbits)  // nbits <= 64
+  {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(words) + (bitpos >> 6);
+    const uint32_t sh = (uint32_t)(bitpos & 63);
+    buf = __ldg(w) >> sh;
+    if (sh + nbits > 64)  // (never touch a word the stream may not own)
+      buf |= __ldg(w + 1) << (64 - sh);
+    buf &= lowmask64(nbits);
+  }
+  __device__ __forceinline__ uint64_t peek(uint32_t len) const { return buf & lowmask64(len); }
+  __device__ __forceinline__ void skip(uint32_t len) { buf = shr64c(buf, len); }
+  __device__ __forceinline__ uint64_t get(uint32_t len)
+  {
+    const uint64_t v = peek(len);
+    skip(len);
+    return v;
+  }
+};
+
 // Column reader (plane-lockstep fixed-rate path): the block's words sit in a lane-private
 // [word][lane] column followed by zero words; reads are by bit position straight from shared memory
 // (no register window to maintain), so all loads of a plane are issued together.
@@ -1210,8 +1235,8 @@ __device__ __forceinline__ void encode_planes_lockstep(ColWriter& bw, uint32_t l
 
 // Mirror image.  Decoded planes are stored to sp[k*32]; returns bits consumed and, through
 // kstop, the lowest plane index that was written.
-template <int N, int P>
-__device__ __forceinline__ uint32_t decode_planes(BitReader& br, uint32_t budget, uint32_t maxprec,
+template <int N, int P, class Reader>
+__device__ __forceinline__ uint32_t decode_planes(Reader& br, uint32_t budget, uint32_t maxprec,
                                                   typename PlaneWord<N>::type* sp, int& kstop)
 {
   const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
@@ -1246,33 +1271,41 @@ __device__ __forceinline__ uint32_t decode_planes(BitReader& br, uint32_t budget
 // Blocks of four values with the table (br.lut4): the planes are not stored and transposed afterwards (64 plane
 // words and two 32 x 32 transposes for at most 4 x 64 bits) - each decoded plane's four bits go straight into the
 // four coefficients.  Returns the bits consumed; u = coefficients ^ NegaWord<NEG> like from_planes<NEG>.
-template <int P, int NEG, class UInt>
-__device__ __forceinline__ uint32_t decode_planes4_direct(BitReader& br, uint32_t budget, uint32_t maxprec, UInt (&u)[4])
+template <int P, int NEG, class UInt, class Reader>
+__device__ __forceinline__ uint32_t decode_planes4_direct(Reader& br, uint32_t budget, uint32_t maxprec, UInt (&u)[4])
 {
   const int kmin = P > (int)maxprec ? P - (int)maxprec : 0;
   uint32_t bits = budget, n = 0;
-  UInt c0 = 0, c1 = 0, c2 = 0, c3 = 0, kbit = (UInt)1 << (P - 1);
-  for (int k = P - 1; bits && k >= kmin; k--, kbit >>= 1) {
-    const uint32_t m = n < bits ? n : bits, left = bits - m, a = left < 7 ? left : 7;
-    const uint32_t w = (uint32_t)br.peek(m + a);
-    const uint32_t ones = (1u << a) - 1;
-    uint32_t e;
-    asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(br.lut4 + ((5u * ones + (n << a) + ((w >> m) & ones)) << 1)));
-    const uint32_t used = m + (e & 15u);
-    br.skip(used);
-    bits -= used;
-    n = e >> 8;
-    const uint32_t x = (w & ((1u << m) - 1)) | ((e >> 4) & 15u);
-    c0 |= (x & 1u) ? kbit : (UInt)0;
-    c1 |= (x & 2u) ? kbit : (UInt)0;
-    c2 |= (x & 4u) ? kbit : (UInt)0;
-    c3 |= (x & 8u) ? kbit : (UInt)0;
+  // (32 bits of the coefficients at a time: the planes of the upper half first)
+  uint32_t c[P / 32][4] = {};
+#pragma unroll
+  for (int h = P / 32 - 1; h >= 0; h--) {
+    uint32_t kbit = 0x80000000u;
+    const int klo = 32 * h > kmin ? 32 * h : kmin;
+    for (int k = 32 * h + 31; bits && k >= klo; k--, kbit >>= 1) {
+      const uint32_t m = n < bits ? n : bits, left = bits - m, a = left < 7 ? left : 7;
+      const uint32_t w = (uint32_t)br.peek(m + a);
+      const uint32_t ones = (1u << a) - 1;
+      uint32_t e;
+      asm("ld.shared.u16 %0, [%1];" : "=r"(e) : "r"(br.lut4 + ((5u * ones + (n << a) + ((w >> m) & ones)) << 1)));
+      const uint32_t used = m + (e & 15u);
+      br.skip(used);
+      bits -= used;
+      n = e >> 8;
+      const uint32_t x = (w & ((1u << m) - 1)) | ((e >> 4) & 15u);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        c[h][i] |= (x >> i) & 1u ? kbit : 0u;
+    }
   }
   constexpr UInt mask = (UInt)NegaWord<NEG>::w64;
-  u[0] = c0 ^ mask;
-  u[1] = c1 ^ mask;
-  u[2] = c2 ^ mask;
-  u[3] = c3 ^ mask;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    UInt v = (UInt)c[0][i];
+    if constexpr (P == 64)
+      v |= (UInt)((uint64_t)c[P / 32 - 1][i] << 32);
+    u[i] = v ^ mask;
+  }
   return budget - bits;
 }
 

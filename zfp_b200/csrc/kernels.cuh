@@ -570,11 +570,25 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   if (b_list >= block1)
     return;
   const uint64_t b = g.box ? box_block(g, b_list) : b_list;
-  BitReader br;
-  br.init(in, OFFS ? offsets[b] : start_bit + b * (uint64_t)prm.maxbits);
-  br.lut4 = lut4;
+  const uint64_t bitpos = OFFS ? offsets[b] : start_bit + b * (uint64_t)prm.maxbits;
   typename TR::Scalar v[N];
-  const uint32_t bits = decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  uint32_t bits = 0;
+  bool small = false;
+  if constexpr (N == 4) {
+    if (prm.maxbits <= 64) {  // the whole block in a register pair
+      SmallReader br;
+      br.init(in, bitpos, prm.maxbits);
+      br.lut4 = lut4;
+      bits = decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+      small = true;
+    }
+  }
+  if (!small) {
+    BitReader br;
+    br.init(in, bitpos);
+    br.lut4 = lut4;
+    bits = decode_block<TYPE, DIMS, REV>(v, prm, br, sp);
+  }
   if (OFFS == 1 && check && lengths && bits != lengths[b])
     atomicOr(check, 1u);
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
