@@ -69,7 +69,7 @@ cudaError_t run_encode_staged(const EncodeArgs& a)
       return run_encode_q4<TYPE>(a);
   }
   auto kernel = encode_staged_kernel<TYPE, DIMS, REV>;
-  constexpr int threads = EncCfg<TYPE>::threads;
+  constexpr int threads = SEncCfg<TYPE, DIMS>::threads;
   const size_t smem = (size_t)(threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                 ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4) +
                       (((ZB_SMALL8 && N == 64 && Traits<TYPE>::P == 64 && !REV) || (N == 16 && !REV)) ? kEncLut8Words * 4 : 0) +
@@ -232,14 +232,14 @@ cudaError_t run_decode_staged(const DecodeArgs& a)
       return run_decode_ws<TYPE>(a);
   }
   auto kernel = decode_staged_kernel<TYPE, DIMS, REV>;
-  const size_t smem = (size_t)(DecCfg<TYPE>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
+  const size_t smem = (size_t)(SDecCfg<TYPE, DIMS>::threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                  ((a.prm.maxbits >> 5) + kReadSlack) * 32 * 4) +
                       (kDecSmall8<N, REV> ? kDecLut8hBytes : 0) + smem_pad();
   static size_t granted[64] = { 0 };  // per kernel instance
   cudaError_t e = allow_smem_cached(kernel, smem, granted);
   if (e != cudaSuccess) return e;
-  const uint64_t ctas = (a.b1 - a.b0 + DecCfg<TYPE>::threads - 1) / DecCfg<TYPE>::threads;
-  kernel<<<(unsigned)ctas, DecCfg<TYPE>::threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
+  const uint64_t ctas = (a.b1 - a.b0 + SDecCfg<TYPE, DIMS>::threads - 1) / SDecCfg<TYPE, DIMS>::threads;
+  kernel<<<(unsigned)ctas, SDecCfg<TYPE, DIMS>::threads, smem, a.st>>>(static_cast<typename Traits<TYPE>::Scalar*>(a.data), a.g, a.prm,
                                                     static_cast<const uint64_t*>(a.in), a.start_bit, a.b0, a.b1);
   return cudaGetLastError();
 }

@@ -269,11 +269,21 @@ template <int TYPE> struct EncCfg {
     return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? ZB_REV32_CTAS : 9) * 64 / threads;
   }
 };
+// the staged kernels' CTA shape: 2-D blocks of 32-bit values carry a 9-10 KB table per CTA (encode_planes_small8 /
+// decode_pair_small8), so their CTAs are larger (8 warps share one copy; 4 CTAs per SM)
+#ifndef ZB_STAGED32_2D_THREADS
+#define ZB_STAGED32_2D_THREADS 256
+#endif
+template <int TYPE, int DIMS> struct SEncCfg {
+  static constexpr bool wide = Traits<TYPE>::P == 32 && DIMS == 2;
+  static constexpr int threads = wide ? ZB_STAGED32_2D_THREADS : EncCfg<TYPE>::threads;
+  __host__ __device__ static constexpr int min_ctas(bool rev) { return wide ? 1024 / ZB_STAGED32_2D_THREADS : EncCfg<TYPE>::min_ctas(rev); }
+};
 constexpr int kStageSlack = 10;   // words of overshoot room: a plane may exceed the budget by < 200 bits and an append stores two words ahead
 constexpr int kStagedPlanes = 32;  // plane words resident at a time in the lockstep kernels (a 32-plane half or a 16-plane window)
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(EncCfg<TYPE>::threads, EncCfg<TYPE>::min_ctas(REV))
+__global__ void __launch_bounds__(SEncCfg<TYPE, DIMS>::threads, SEncCfg<TYPE, DIMS>::min_ctas(REV))
 encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      uint64_t* __restrict__ out, uint64_t start_bit)
 {
@@ -293,7 +303,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
 
   // no early exit: lanes past the end redo the last block and discard it, so that warp-wide votes
   // inside encode_block always see 32 lanes
-  const uint64_t b_raw = (uint64_t)blockIdx.x * EncCfg<TYPE>::threads + threadIdx.x;
+  const uint64_t b_raw = (uint64_t)blockIdx.x * SEncCfg<TYPE, DIMS>::threads + threadIdx.x;
   const bool valid = b_raw < g.nblocks;
   const uint64_t b = valid ? b_raw : g.nblocks - 1;
   const BlockPos<DIMS> pos = locate<DIMS>(g, b);
@@ -303,7 +313,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   if constexpr (N == 64 && TR::P == 64) {
     uint32_t nsm;
     asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-    constexpr int kWaveThreads = EncCfg<TYPE>::min_ctas(REV) * EncCfg<TYPE>::threads;  // per multiprocessor
+    constexpr int kWaveThreads = SEncCfg<TYPE, DIMS>::min_ctas(REV) * SEncCfg<TYPE, DIMS>::threads;  // per multiprocessor
     prefetch_block<DIMS>(data, g, b_raw + (uint64_t)nsm * kWaveThreads);
   }
 #endif
@@ -312,22 +322,22 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
   bw.init(stage);
   if constexpr (N == 4) {
     // the plane-string table of the 4-value blocks (kEncLut4), one copy per CTA behind the warps' buffers
-    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (EncCfg<TYPE>::threads / 32) * warp_bytes);
-    for (int i = threadIdx.x; i < kEncLut4Words; i += EncCfg<TYPE>::threads)
+    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (SEncCfg<TYPE, DIMS>::threads / 32) * warp_bytes);
+    for (int i = threadIdx.x; i < kEncLut4Words; i += SEncCfg<TYPE, DIMS>::threads)
       lut[i] = kEncLut4[i];
     __syncthreads();
     bw.lut = (uint32_t)__cvta_generic_to_shared(lut);
   }
   if constexpr ((ZB_SMALL8 && N == 64 && TR::P == 64 && !REV) || (N == 16 && !REV)) {
     // the table of the small-universe plane steps (encode_planes_small8), one copy per CTA
-    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (EncCfg<TYPE>::threads / 32) * warp_bytes);  // (behind the warps' buffers)
-    for (int i = threadIdx.x; i < kEncLut8Words / 4; i += EncCfg<TYPE>::threads)
+    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (SEncCfg<TYPE, DIMS>::threads / 32) * warp_bytes);  // (behind the warps' buffers)
+    for (int i = threadIdx.x; i < kEncLut8Words / 4; i += SEncCfg<TYPE, DIMS>::threads)
       reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(kEncLut8) + i);
     __syncthreads();
     bw.lut = (uint32_t)__cvta_generic_to_shared(lut);
   }
 #if ZB_ENC_SYNC
-  encode_block<TYPE, DIMS, REV, ColWriter, (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) ? EncCfg<TYPE>::threads / 4 : 0>(v, prm, bw, sp);
+  encode_block<TYPE, DIMS, REV, ColWriter, (Traits<TYPE>::P == 64 && DIMS == 3 && !REV) ? SEncCfg<TYPE, DIMS>::threads / 4 : 0>(v, prm, bw, sp);
 #else
   encode_block<TYPE, DIMS, REV>(v, prm, bw, sp);
 #endif
@@ -370,6 +380,11 @@ template <int TYPE> struct DecCfg {
   static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_DEC64_THREADS : ZB_DEC32_THREADS;
   static constexpr int min_ctas(bool rev) { return Traits<TYPE>::P == 64 ? 384 / ZB_DEC64_THREADS : (rev ? ZB_REV32_CTAS : 9) * 64 / ZB_DEC32_THREADS; }
 };
+template <int TYPE, int DIMS> struct SDecCfg {
+  static constexpr bool wide = Traits<TYPE>::P == 32 && DIMS == 2;
+  static constexpr int threads = wide ? ZB_STAGED32_2D_THREADS : DecCfg<TYPE>::threads;
+  __host__ __device__ static constexpr int min_ctas(bool rev) { return wide ? 1024 / ZB_STAGED32_2D_THREADS : DecCfg<TYPE>::min_ctas(rev); }
+};
 // table-driven plane steps while only coefficients 0..7 are significant (decode_pair_small8): 2-D blocks;
 // 3-D blocks with -DZB_DSMALL8_3D=1 (experiment)
 #ifndef ZB_DSMALL8_3D
@@ -379,7 +394,7 @@ template <int N, bool REV> constexpr bool kDecSmall8 = !REV && (N == 16 || (ZB_D
 constexpr int kReadSlack = 5;  // zero words after the block: a plane's reads reach 64 + 32 bits past the position, rounded up to words
 
 template <int TYPE, int DIMS, bool REV>
-__global__ void __launch_bounds__(DecCfg<TYPE>::threads, DecCfg<TYPE>::min_ctas(REV))
+__global__ void __launch_bounds__(SDecCfg<TYPE, DIMS>::threads, SDecCfg<TYPE, DIMS>::min_ctas(REV))
 decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params prm,
                      const uint64_t* __restrict__ in, uint64_t start_bit, uint64_t block0, uint64_t block1)
 {
@@ -401,7 +416,7 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   PW* sp = reinterpret_cast<PW*>(reinterpret_cast<char*>(smem_raw) + sp_off);
   uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + stage_off);
 
-  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * DecCfg<TYPE>::threads + threadIdx.x;
+  const uint64_t b_raw = block0 + (uint64_t)blockIdx.x * SDecCfg<TYPE, DIMS>::threads + threadIdx.x;
   const bool valid = b_raw < block1;  // no early exit (warp-wide votes in decode_block)
   const uint64_t b_list = valid ? b_raw : block1 - 1;
   const uint64_t b = g.box ? box_block(g, b_list) : b_list;
@@ -439,8 +454,8 @@ decode_staged_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, P
   br.set_run_table(run_table);
   if constexpr (kDecSmall8<N, REV>) {
     // the table of the small-universe plane steps (decode_pair_small8), one copy per CTA behind the warps' buffers
-    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (DecCfg<TYPE>::threads / 32) * warp_bytes);
-    for (int i = threadIdx.x; i < kDecLut8hBytes / 16; i += DecCfg<TYPE>::threads)
+    uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (SDecCfg<TYPE, DIMS>::threads / 32) * warp_bytes);
+    for (int i = threadIdx.x; i < kDecLut8hBytes / 16; i += SDecCfg<TYPE, DIMS>::threads)
       reinterpret_cast<uint4*>(lut)[i] = __ldg(reinterpret_cast<const uint4*>(kDecLut8h) + i);
     __syncthreads();
     br.lut8 = (uint32_t)__cvta_generic_to_shared(lut);
