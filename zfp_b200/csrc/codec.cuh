@@ -2039,8 +2039,8 @@ __device__ __forceinline__ uint32_t encode_block(const typename Traits<TYPE>::Sc
     }
     else {
       int ksmall = 32;
-      const int kup = to_planes_half<0, NEG, UInt, N>(u, sp, (N == 16 && !REV && bw.lut) ? &ksmall : nullptr);
-      if constexpr (N == 16 && !REV)
+      const int kup = to_planes_half<0, NEG, UInt, N>(u, sp, ((N == 16 || N == 64) && !REV && bw.lut) ? &ksmall : nullptr);
+      if constexpr ((N == 16 || N == 64) && !REV)
         if (bw.lut)
           encode_planes_small8<N>(bw, limit, kmin, 0, ksmall, st, sp);
       encode_planes_lockstep<N>(bw, limit, kmin, 0, 0, st, sp, kup);
@@ -2106,7 +2106,8 @@ __device__ __forceinline__ void wg_leave_large()
 
 // PS > 0 (kernels_ps.cuh, blocks of 64 64-bit values): the caller's warpgroup holds a small register
 // budget while it parses planes 63..32 and acquires PS registers per thread before the first transposes.
-template <int TYPE, int DIMS, bool REV, class Reader, int PS = 0>
+// LENGTH_ONLY (serial readers): parse the block for its length and skip transposes, transform and cast (index rebuild).
+template <int TYPE, int DIMS, bool REV, class Reader, int PS = 0, bool LENGTH_ONLY = false>
 __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (&v)[1 << (2 * DIMS)],
                                                  const Params& prm, Reader& br,
                                                  typename PlaneWord<(1 << (2 * DIMS))>::type* sp)
@@ -2228,7 +2229,8 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     if (!direct) {
       int kstop;
       bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
-      from_planes<NEG, UInt, N>(u, sp, kstop);
+      if constexpr (!LENGTH_ONLY)
+        from_planes<NEG, UInt, N>(u, sp, kstop);
     }
   }
   else {
@@ -2240,6 +2242,8 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     bits = 1;
   if (bits < prm.minbits)
     bits = prm.minbits;
+  if constexpr (LENGTH_ONLY)
+    return bits;
 
   Int q[N];
 #pragma unroll

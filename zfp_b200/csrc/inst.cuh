@@ -72,7 +72,7 @@ cudaError_t run_encode_staged(const EncodeArgs& a)
   constexpr int threads = SEncCfg<TYPE, DIMS>::threads;
   const size_t smem = (size_t)(threads / 32) * (kStagedPlanes * 32 * sizeof(typename PlaneWord<N>::type) +
                                                 ((a.prm.maxbits >> 5) + kStageSlack) * 32 * 4) +
-                      (((ZB_SMALL8 && N == 64 && Traits<TYPE>::P == 64 && !REV) || (N == 16 && !REV)) ? kEncLut8Words * 4 : 0) +
+                      (kEncSmall8<TYPE, N, REV> ? kEncLut8Words * 4 : 0) +
                       (N == 4 ? kEncLut4Words * 4 : 0) + smem_pad();
   static size_t granted[64] = { 0 };  // per kernel instance
   cudaError_t e = allow_smem_cached(kernel, smem, granted);

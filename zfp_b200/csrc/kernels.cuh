@@ -249,6 +249,9 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_SMALL8
 #define ZB_SMALL8 0
 #endif
+#ifndef ZB_SMALL8_F32
+#define ZB_SMALL8_F32 0  // the same steps for 3-D blocks of 32-bit values (experiment)
+#endif
 #ifndef ZB_REV32_CTAS
 #define ZB_REV32_CTAS 6  // CTAs of 64 threads per SM the reversible 32-bit kernels are compiled for (register cap 170)
 #endif
@@ -261,6 +264,9 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_ENC_SYNC
 #define ZB_ENC_SYNC 0  // 1 with ZB_ENC64_THREADS = 256 / 384: warps on one scheduler rendezvous before the long stages
 #endif
+// kernels that carry the encoder's 8-coefficient table (encode_planes_small8): 2-D blocks; 3-D blocks by experiment switch
+template <int TYPE, int N, bool REV>
+constexpr bool kEncSmall8 = !REV && (N == 16 || (N == 64 && (Traits<TYPE>::P == 64 ? ZB_SMALL8 : ZB_SMALL8_F32)));
 template <int TYPE> struct EncCfg {
   static constexpr int threads = Traits<TYPE>::P == 64 ? ZB_ENC64_THREADS : ZB_ENC32_THREADS;
   __host__ __device__ static constexpr int min_ctas(bool rev)
@@ -328,7 +334,7 @@ encode_staged_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geo
     __syncthreads();
     bw.lut = (uint32_t)__cvta_generic_to_shared(lut);
   }
-  if constexpr ((ZB_SMALL8 && N == 64 && TR::P == 64 && !REV) || (N == 16 && !REV)) {
+  if constexpr (kEncSmall8<TYPE, N, REV>) {
     // the table of the small-universe plane steps (encode_planes_small8), one copy per CTA
     uint32_t* lut = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(smem_raw) + (SEncCfg<TYPE, DIMS>::threads / 32) * warp_bytes);  // (behind the warps' buffers)
     for (int i = threadIdx.x; i < kEncLut8Words / 4; i += SEncCfg<TYPE, DIMS>::threads)
@@ -627,7 +633,7 @@ __global__ void index_scan_kernel(const void* __restrict__ in, uint64_t start_bi
     BitReader br;
     br.init(in, pos);
     typename TR::Scalar v[N];
-    const uint32_t bits = decode_block<TYPE, DIMS, REV>(v, prm, br, planes);
+    const uint32_t bits = decode_block<TYPE, DIMS, REV, BitReader, 0, true>(v, prm, br, planes);  // (length only)
     lengths[b] = (uint16_t)bits;
     pos += bits;
   }
