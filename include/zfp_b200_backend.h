@@ -161,6 +161,15 @@ size_t zfp_b200_index_blocks(const zfp_b200_index* index);
 uint64 zfp_b200_index_bits(const zfp_b200_index* index);
 /* serialised form: 16-bit coded length per block, block order = stream order */
 size_t zfp_b200_index_export(const zfp_b200_index* index, uint16_t* host_lengths, size_t capacity);
+/* Rebuild the index of a variable-rate stream that arrived without one (a file written by another zfp), in parallel:
+ * the stream in [d_words, d_words + words_bytes) is cut into segments that are parsed speculatively and stitched
+ * (a parse that starts off a block boundary falls onto the true chain of blocks after a few hundred blocks).  The
+ * result is treated like an imported index: the decode checks every length and falls back to walking the stream
+ * sequentially (~6 us per block) if it does not hold.  ZFP_B200_EINVAL when not applicable (fixed rate, 4-D, fewer
+ * than 16384 blocks or less than 4 Mbit of stream): decode with index == NULL then.  zfp_decompress does this by itself for host-API callers, whose
+ * bitstream knows where its buffer ends. */
+int zfp_b200_index_rebuild(const zfp_b200_desc* desc, const void* d_words, uint64 start_bit, size_t words_bytes,
+                           zfp_b200_index* index, void* cuda_stream);
 int zfp_b200_index_import(zfp_b200_index* index, const uint16_t* host_lengths, size_t blocks);
 
 /* ---- diagnostics --------------------------------------------------------------------------------- */

@@ -279,6 +279,38 @@ def test_foreign_variable_rate_stream_without_index(zb, port, ref):
             assert got.tobytes() == want.tobytes(), (shape, mode)
 
 
+def test_foreign_stream_index_rebuilt_in_parallel(zb, port, monkeypatch):
+    """From 16384 blocks on, zfp_decompress rebuilds the index of a stream that came without one segment-parallel
+    (speculative walks stitched at block boundaries, zfp_b200_index_rebuild) instead of with one thread; the decode
+    verifies the candidate.  Same result as the oracle and as the sequential walk, in a fraction of its time."""
+    import time
+    cases = [(np.float64, (160, 160, 164), {"accuracy": 1e-7}), (np.float64, (160, 160, 164), {"precision": 28}),
+             (np.float32, (2048, 2052), {"reversible": True}), (np.int64, (1200000,), {"precision": 40}),
+             (np.float64, (160, 156, 164), {"expert": (40, 900, 40, -40)})]
+    for dtype, shape, mode in cases:
+        a = make_field(shape, dtype, seed=31, kind="smooth")
+        a.reshape(-1)[: a.size // 5] = 0                     # a run of empty blocks: one bit each
+        words = port.compress(a, **mode)
+        want = port.decompress(words, a.shape, a.dtype, **mode)
+        n0 = zb.launch_count()
+        t0 = time.perf_counter()
+        got, used = zb.decompress_numpy(words, a.shape, a.dtype, index=None, **mode)
+        t_par = time.perf_counter() - t0
+        launches_par = zb.launch_count() - n0
+        assert used == words.nbytes and got.tobytes() == want.tobytes(), (shape, mode)
+        monkeypatch.setenv("ZFP_B200_SERIAL_INDEX", "1")
+        n0 = zb.launch_count()
+        t0 = time.perf_counter()
+        got2, _ = zb.decompress_numpy(words, a.shape, a.dtype, index=None, **mode)
+        t_ser = time.perf_counter() - t0
+        launches_ser = zb.launch_count() - n0
+        monkeypatch.delenv("ZFP_B200_SERIAL_INDEX")
+        assert got2.tobytes() == want.tobytes()
+        assert words.nbytes * 8 >= 1 << 23, "test case too small for the parallel rebuild"
+        assert launches_par > launches_ser, "the parallel rebuild did not run"
+        assert t_par < 0.6 * t_ser, (shape, mode, t_par, t_ser)
+
+
 def test_untrusted_block_index_cannot_mislead_the_decoder(zb, port):
     """A block index that comes from outside (zfp_b200_index_import, the zfpy trailer) with lengths that
     are wrong - every block at the 16-bit maximum, all zero, or those of another field - must neither

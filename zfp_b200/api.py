@@ -101,6 +101,7 @@ _PROTOTYPES = {
     "zfp_b200_capacity": (_sz, [C.POINTER(Desc), C.c_uint64]),
     "zfp_b200_index_create": (_vp, []), "zfp_b200_index_destroy": (None, [_vp]), "zfp_b200_index_bits": (C.c_uint64, [_vp]),
     "zfp_b200_index_blocks": (_sz, [_vp]), "zfp_b200_index_export": (_sz, [_vp, _vp, _sz]),
+    "zfp_b200_index_rebuild": (C.c_int, [_vp, _vp, C.c_uint64, _sz, _vp, _vp]),
     "zfp_b200_index_import": (C.c_int, [_vp, _vp, _sz]),
     "zfp_b200_last_error": (C.c_char_p, []), "zfp_b200_launch_count": (C.c_uint64, []),
     "zfp_b200_release_scratch": (None, []),

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -163,6 +164,7 @@ struct zfp_b200_index {
   size_t blocks = 0;
   size_t capacity = 0;
   uint64_t total_bits = 0;  // sum of the lengths, recorded by the encode that filled the index
+  bool speculative = false; // made by zfp_b200_index_rebuild for whatever stream was decoded last: never reused as is
   // what the lengths describe (filled by zfp_b200_encode): a decode with other parameters or another
   // start phase ignores the index and rebuilds one; a decode that finds a block whose parsed length
   // differs from the recorded one (same shape and parameters, other data) reports it and is redone
@@ -222,6 +224,7 @@ extern "C" int zfp_b200_index_import(zfp_b200_index* ix, const uint16_t* host, s
   if (!index_reserve(ix, blocks)) return ZFP_B200_ECUDA;
   CU(cudaMemcpy(ix->d_lengths, host, blocks * sizeof(uint16_t), cudaMemcpyHostToDevice));
   ix->keyed = false;
+  ix->speculative = false;
   ix->total_bits = 0;
   return ZFP_B200_OK;
 }
@@ -465,6 +468,7 @@ static int encode_var1(const zfp_b200_desc* d, const Geom& g, const Params& prm,
   if ((rc = launch_var1(type, a, v))) return rc;
   if (index) {
     index->keyed = true;
+    index->speculative = false;
     index->key_desc = *d;
     index->key_start = start_bit;
     index->total_bits = 0;
@@ -603,6 +607,7 @@ static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words
   }
   if (index) {
     index->keyed = true;
+    index->speculative = false;
     index->key_desc = *d;
     index->key_start = start_bit;
     index->total_bits = 0;
@@ -623,6 +628,93 @@ static int encode_impl(const zfp_b200_desc* d, const void* d_data, void* d_words
 static int decode_range(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit, uint64* end_bit,
                         const zfp_b200_index* index, void* cuda_stream, uint64_t block0, uint64_t block1, bool whole,
                         uint32_t* d_status = nullptr, const size_t* box_lo = nullptr, const size_t* box_hi = nullptr);
+
+// Candidate block index of a variable-rate stream that came without one, rebuilt segment-parallel (kernels.cuh
+// spec_index_kernel).  The caller says where the buffer ends (words_bytes from d_words): speculative walks start
+// anywhere in it and must not read beyond.  The index is marked "imported": the decode verifies it block by block
+// and falls back to the sequential rebuild if it is wrong.  Returns ZFP_B200_EINVAL when the case is not covered
+// (4-D, few blocks, fixed rate) - the caller then simply decodes without an index.
+extern "C" int zfp_b200_index_rebuild(const zfp_b200_desc* d, const void* d_words, uint64 start_bit, size_t words_bytes,
+                                      zfp_b200_index* index, void* cuda_stream)
+{
+  Geom g;
+  if (!index || !d_words || !make_geom(d, d_words, &g) || !check_params(d)) return ZFP_B200_EINVAL;
+  if (d->minbits == d->maxbits || d->dims > 3 || g.nblocks < 16384) return ZFP_B200_EINVAL;
+  const uint64_t avail = (uint64_t)words_bytes * 8;
+  const uint32_t cap = block_capacity_bits(d), margin = cap + 128;
+  if (avail <= start_bit + margin) return ZFP_B200_EINVAL;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ScratchLease lease(st);
+  // A walk that starts off a block boundary lands on one with probability ~1 / (bits per block) per garbage block,
+  // i.e. after some 10^5 bits; segments are an order of magnitude longer, so that a walk has almost surely met the
+  // true chain when it leaves its segment (if not, pass 1 repeats; after 8 rounds the sequential walk takes over).
+  uint64_t seg = (avail - start_bit + 65535) / 65536;   // at most 65536 segments ...
+  if (seg < (1ull << 20)) seg = 1ull << 20;              // ... of at least 1 Mbit
+  if (seg < 256ull * cap) seg = 256ull * cap;
+  const uint32_t nseg = (uint32_t)((avail - start_bit + seg - 1) / seg);
+  if (nseg < 4) return ZFP_B200_EINVAL;                  // (too short to gain anything)
+  if (!index_reserve(index, g.nblocks)) return ZFP_B200_ECUDA;
+  uint64_t *d_exit = nullptr, *d_off = nullptr;
+  uint32_t* d_cnt = nullptr;
+  std::vector<uint32_t> h_cnt(nseg);
+  std::vector<uint64_t> h_off(nseg);
+  int rc = ZFP_B200_ECUDA;
+  auto launch = [&](int pass, const SpecIndexArgs& a) -> cudaError_t {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    switch (d->type) {
+      case T_INT32: return launch_spec_index_t<T_INT32>((int)d->dims, pass, a, st);
+      case T_INT64: return launch_spec_index_t<T_INT64>((int)d->dims, pass, a, st);
+      case T_FLOAT: return launch_spec_index_t<T_FLOAT>((int)d->dims, pass, a, st);
+      default: return launch_spec_index_t<T_DOUBLE>((int)d->dims, pass, a, st);
+    }
+  };
+  do {
+    if (cudaMalloc(&d_exit, (size_t)nseg * 8) != cudaSuccess || cudaMalloc(&d_off, (size_t)nseg * 8) != cudaSuccess ||
+        cudaMalloc(&d_cnt, (size_t)nseg * 4 + 4) != cudaSuccess) break;
+    uint32_t* d_changed = d_cnt + nseg;
+    const Params prm = { d->minbits, d->maxbits, d->maxprec, d->minexp };
+    SpecIndexArgs a = { d_words, start_bit, avail, seg, nseg, margin, prm, d_exit, d_cnt, d_changed, d_off, index->d_lengths, g.nblocks };
+    if (!cuda_ok(launch(0, a), "index rebuild, pass 0")) break;
+    bool settled = false;
+    for (int it = 0; it < 8 && !settled; it++) {
+      uint32_t changed = 0;
+      if (cudaMemsetAsync(d_changed, 0, 4, st) != cudaSuccess || !cuda_ok(launch(1, a), "index rebuild, pass 1")) break;
+      if (cudaMemcpyAsync(&changed, d_changed, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) break;
+      settled = !changed;
+    }
+    if (!settled) { rc = ZFP_B200_EINVAL; break; }
+    if (cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)nseg * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) break;
+    uint64_t total = 0;
+    for (uint32_t t = 0; t < nseg; t++) { h_off[t] = total; total += h_cnt[t]; }
+    if (cudaMemcpyAsync(d_off, h_off.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) break;
+    if (!cuda_ok(launch(2, a), "index rebuild, pass 2")) break;
+    if (total < g.nblocks) {
+      // the walks stop a worst-case block short of the buffer's end: the sequential walk finishes from there
+      uint64_t last = 0;
+      if (cudaMemcpyAsync(&last, d_exit + (nseg - 1), 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) break;
+      const DecodeArgs da = { nullptr, g, prm, d_words, last, nullptr, nullptr, st, 0, total, g.nblocks, nullptr };
+      cudaError_t e;
+      switch (d->type) {
+        case T_INT32: e = launch_index_t<T_INT32>((int)d->dims, da, index->d_lengths); break;
+        case T_INT64: e = launch_index_t<T_INT64>((int)d->dims, da, index->d_lengths); break;
+        case T_FLOAT: e = launch_index_t<T_FLOAT>((int)d->dims, da, index->d_lengths); break;
+        default: e = launch_index_t<T_DOUBLE>((int)d->dims, da, index->d_lengths); break;
+      }
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (!cuda_ok(e, "index rebuild, tail")) break;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) break;
+    index->keyed = false;
+    index->total_bits = 0;
+    index->speculative = true;
+    rc = ZFP_B200_OK;
+  } while (false);
+  cudaFree(d_exit);
+  cudaFree(d_off);
+  cudaFree(d_cnt);
+  if (rc != ZFP_B200_OK) index->blocks = 0;
+  return rc;
+}
 
 extern "C" int zfp_b200_decode(const zfp_b200_desc* d, void* d_data, const void* d_words, uint64 start_bit,
                                uint64* end_bit, const zfp_b200_index* index, void* cuda_stream)
@@ -1302,8 +1394,30 @@ static size_t decompress_impl(zfp_stream* zfp, zfp_field* field)
   }
 
   const zfp_b200_index* index = (d.minbits != d.maxbits && xp) ? xp->index : nullptr;
+  zfp_b200_index* own_index = nullptr;  // (a zfp_stream without CUDA parameters has no place to keep one)
+  if (d.minbits != d.maxbits && s->end > s->begin + first_word && !getenv("ZFP_B200_SERIAL_INDEX")) {
+    // a stream that did not come from this zfp_stream: rebuild a candidate index in parallel (the bit stream says
+    // where its buffer ends); the decode verifies it and walks the stream sequentially if it does not hold
+    Geom g;
+    if (make_geom(&d, d_data, &g) && (!index_matches(index, &d, g, start_bit & 63) || index->speculative)) {
+      zfp_b200_index* target;
+      if (xp) {
+        if (!xp->index) xp->index = zfp_b200_index_create();
+        target = xp->index;
+      }
+      else
+        target = own_index = zfp_b200_index_create();
+      const size_t have = (size_t)(s->end - (s->begin + first_word)) * 8;
+      size_t avail = zfp_b200_capacity(&d, start_bit & 63);
+      if (avail > have) avail = have;
+      index = (target && zfp_b200_index_rebuild(&d, d_words, start_bit & 63, avail, target, st) == ZFP_B200_OK) ? target : nullptr;
+      g_error.clear();
+    }
+  }
   uint64_t end_rel = 0;
-  if (zfp_b200_decode(&d, d_data, d_words, start_bit & 63, &end_rel, index, st) != ZFP_B200_OK) return 0;
+  const int decoded = zfp_b200_decode(&d, d_data, d_words, start_bit & 63, &end_rel, index, st);  // (variable rate: synchronous)
+  zfp_b200_index_destroy(own_index);
+  if (decoded != ZFP_B200_OK) return 0;
 
   if (!data_dev)
     if (!cuda_ok(cudaMemcpyAsync(static_cast<char*>(field->data) + lo * (int64_t)esize, stage, span_bytes,

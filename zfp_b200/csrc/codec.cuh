@@ -1235,7 +1235,7 @@ __device__ __forceinline__ void encode_planes_lockstep(ColWriter& bw, uint32_t l
 
 // Mirror image.  Decoded planes are stored to sp[k*32]; returns bits consumed and, through
 // kstop, the lowest plane index that was written.
-template <int N, int P, class Reader>
+template <int N, int P, class Reader, bool STORE = true>
 __device__ __forceinline__ uint32_t decode_planes(Reader& br, uint32_t budget, uint32_t maxprec,
                                                   typename PlaneWord<N>::type* sp, int& kstop)
 {
@@ -1262,7 +1262,8 @@ __device__ __forceinline__ uint32_t decode_planes(Reader& br, uint32_t budget, u
       x |= 1ull << n;  // deposited even if the scan ran dry (decode.c:103-111)
       n++;
     }
-    sp[k * 32] = (typename PlaneWord<N>::type)x;
+    if constexpr (STORE)
+      sp[k * 32] = (typename PlaneWord<N>::type)x;
   }
   kstop = k + 1;
   return budget - bits;
@@ -2228,7 +2229,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
     }
     if (!direct) {
       int kstop;
-      bits += decode_planes<N, P>(br, prm.maxbits - bits, maxprec, sp, kstop);
+      bits += decode_planes<N, P, Reader, !LENGTH_ONLY>(br, prm.maxbits - bits, maxprec, sp, kstop);  // (length only: sp unused)
       if constexpr (!LENGTH_ONLY)
         from_planes<NEG, UInt, N>(u, sp, kstop);
     }

@@ -375,16 +375,39 @@ cudaError_t launch_index_impl(int dims, const DecodeArgs& a, uint16_t* lengths)
 {
   const bool rev = a.prm.minexp < kMinExp;
   switch (dims) {
-    case 1: if (rev) index_scan_kernel<TYPE, 1, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths);
-            else index_scan_kernel<TYPE, 1, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
-    case 2: if (rev) index_scan_kernel<TYPE, 2, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths);
-            else index_scan_kernel<TYPE, 2, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
-    case 3: if (rev) index_scan_kernel<TYPE, 3, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths);
-            else index_scan_kernel<TYPE, 3, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
-    case 4: index_scan4_kernel<TYPE><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
+    case 1: if (rev) index_scan_kernel<TYPE, 1, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.b0, a.g.nblocks, a.prm, lengths);
+            else index_scan_kernel<TYPE, 1, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.b0, a.g.nblocks, a.prm, lengths); break;
+    case 2: if (rev) index_scan_kernel<TYPE, 2, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.b0, a.g.nblocks, a.prm, lengths);
+            else index_scan_kernel<TYPE, 2, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.b0, a.g.nblocks, a.prm, lengths); break;
+    case 3: if (rev) index_scan_kernel<TYPE, 3, true><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.b0, a.g.nblocks, a.prm, lengths);
+            else index_scan_kernel<TYPE, 3, false><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.b0, a.g.nblocks, a.prm, lengths); break;
+    case 4: if (a.b0) return cudaErrorInvalidValue;
+            index_scan4_kernel<TYPE><<<1, 1, 0, a.st>>>(a.in, a.start_bit, a.g.nblocks, a.prm, lengths); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
+}
+
+template <int TYPE, int DIMS, bool REV>
+cudaError_t launch_spec_index_pass(int pass, const SpecIndexArgs& a, cudaStream_t st)
+{
+  const unsigned ctas = (a.nseg + 1) / 2;  // two walkers (warps) per CTA
+  if (pass == 0) spec_index_kernel<TYPE, DIMS, REV, 0><<<ctas, 64, 0, st>>>(a);
+  else if (pass == 1) spec_index_kernel<TYPE, DIMS, REV, 1><<<ctas, 64, 0, st>>>(a);
+  else spec_index_kernel<TYPE, DIMS, REV, 2><<<ctas, 64, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int TYPE>
+cudaError_t launch_spec_index_impl(int dims, int pass, const SpecIndexArgs& a, cudaStream_t st)
+{
+  const bool rev = a.prm.minexp < kMinExp;
+  switch (dims) {
+    case 1: return rev ? launch_spec_index_pass<TYPE, 1, true>(pass, a, st) : launch_spec_index_pass<TYPE, 1, false>(pass, a, st);
+    case 2: return rev ? launch_spec_index_pass<TYPE, 2, true>(pass, a, st) : launch_spec_index_pass<TYPE, 2, false>(pass, a, st);
+    case 3: return rev ? launch_spec_index_pass<TYPE, 3, true>(pass, a, st) : launch_spec_index_pass<TYPE, 3, false>(pass, a, st);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace zb

@@ -3,4 +3,5 @@
 namespace zb {
 template <> cudaError_t launch_decode_t<4>(int dims, int offs_mode, const DecodeArgs& a) { return launch_decode_impl<4>(dims, offs_mode, a); }
 template <> cudaError_t launch_index_t<4>(int dims, const DecodeArgs& a, uint16_t* lengths) { return launch_index_impl<4>(dims, a, lengths); }
+template <> cudaError_t launch_spec_index_t<4>(int dims, int pass, const SpecIndexArgs& a, cudaStream_t st) { return launch_spec_index_impl<4>(dims, pass, a, st); }
 }

@@ -618,24 +618,78 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
 
 // Index rebuild for a variable-rate stream that arrives without block lengths: block b's position
 // is only known once blocks 0..b-1 have been parsed (the zfp format stores no offsets,
-// docs/source/execution.rst:292-300), so this is inherently sequential: ONE thread walks the stream.
-// Correct but slow; streams produced by this backend carry their index and never come here.
+// docs/source/execution.rst:292-300).  index_scan_kernel is the plain answer: ONE thread walks the stream
+// (length-only parse, 5.5-7 us per block) from block b0 at bit start_bit.  Correct, and slow; streams produced
+// by this backend carry their index and never come here.
 template <int TYPE, int DIMS, bool REV>
-__global__ void index_scan_kernel(const void* __restrict__ in, uint64_t start_bit, uint64_t nblocks, Params prm,
+__global__ void index_scan_kernel(const void* __restrict__ in, uint64_t start_bit, uint64_t b0, uint64_t nblocks, Params prm,
                                   uint16_t* __restrict__ lengths)
 {
   using TR = Traits<TYPE>;
   constexpr int N = 1 << (2 * DIMS);
-  using PW = typename PlaneWord<N>::type;
-  __shared__ PW planes[TR::P * 32];
   uint64_t pos = start_bit;
-  for (uint64_t b = 0; b < nblocks; b++) {
+  for (uint64_t b = b0; b < nblocks; b++) {
     BitReader br;
     br.init(in, pos);
     typename TR::Scalar v[N];
-    const uint32_t bits = decode_block<TYPE, DIMS, REV, BitReader, 0, true>(v, prm, br, planes);  // (length only)
+    const uint32_t bits = decode_block<TYPE, DIMS, REV, BitReader, 0, true>(v, prm, br, nullptr);  // (length only)
     lengths[b] = (uint16_t)bits;
     pos += bits;
+  }
+}
+
+// Speculative segment-parallel rebuild.  A parse that starts at a wrong bit position produces garbage blocks, but
+// each of them ends somewhere, and as soon as one ends on a true block boundary the walk is on the true chain for
+// good; with blocks of a few hundred bits that takes a few hundred blocks.  So: one thread per segment of the
+// stream (segments are much longer than that).
+//   pass 0: walk from the segment's first bit to its end; exit[t] = where the walk left the segment.  For all but
+//           pathological streams the walk has met the true chain by then, so exit[t] is where the true chain
+//           enters segment t + 1.
+//   pass 1: walk segment t from that entry (segment 0: the stream's first block), count the blocks, and check that
+//           the walk leaves through exit[t]; an exit that moves is corrected and the pass repeated.
+//   pass 2: (block numbers now known from a prefix sum of the counts) walk once more and store the lengths.
+// The result is a CANDIDATE: the decode checks every indexed length against what the block parses to and falls
+// back to the sequential rebuild on any mismatch, so a walk that never converged costs time, not correctness.
+// A walk stops margin_bits before the end of the buffer (garbage blocks must not read past it); whatever is left
+// there is finished by index_scan_kernel.
+template <int TYPE, int DIMS, bool REV, int PASS>
+__global__ void __launch_bounds__(64) spec_index_kernel(SpecIndexArgs a)
+{
+  using TR = Traits<TYPE>;
+  constexpr int N = 1 << (2 * DIMS);
+  // one walker per WARP (lane 0): walkers in one warp would diverge at every loop of the parse and run one after the other
+  const uint32_t t = (blockIdx.x * 64 + threadIdx.x) >> 5;
+  if ((threadIdx.x & 31) != 0 || t >= a.nseg)
+    return;
+  const uint64_t seg_begin = a.start_bit + (uint64_t)t * a.seg_bits;
+  uint64_t seg_end = seg_begin + a.seg_bits;
+  const uint64_t stop = a.avail_bits > a.margin_bits ? a.avail_bits - a.margin_bits : 0;  // no walk starts a block beyond this
+  if (t + 1 == a.nseg || seg_end > stop)
+    seg_end = stop;
+  uint64_t pos = (PASS == 0 || t == 0) ? seg_begin : a.exit[t - 1];
+  uint64_t b = PASS == 2 ? a.off[t] : 0;
+  uint32_t n = 0;
+  while (pos < seg_end) {
+    BitReader br;
+    br.init(a.in, pos);
+    typename TR::Scalar v[N];
+    const uint32_t bits = decode_block<TYPE, DIMS, REV, BitReader, 0, true>(v, a.prm, br, nullptr);
+    if (PASS == 2) {
+      if (b < a.nblocks)
+        a.lengths[b] = (uint16_t)bits;
+      b++;
+    }
+    n++;
+    pos += bits ? bits : 1;  // (a block is never empty; guard against a stuck walk on garbage parameters)
+  }
+  if (PASS == 0)
+    a.exit[t] = pos;
+  if (PASS == 1) {
+    a.cnt[t] = n;
+    if (a.exit[t] != pos) {
+      a.exit[t] = pos;
+      *a.changed = 1;
+    }
   }
 }
 

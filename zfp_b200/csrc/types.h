@@ -90,7 +90,26 @@ template <int TYPE> cudaError_t launch_decode_t(int dims, int offs_mode, const D
 // the tile size through *tile_blocks when a == nullptr-like query is wanted (see backend.cu)
 template <int TYPE> cudaError_t launch_encode_var1_t(const EncodeArgs& a, const Var1Bufs& v);
 template <int TYPE> int var1_tile_blocks();
-// sequential rebuild of the block-length index of a variable-rate stream
+// sequential rebuild of the block-length index of a variable-rate stream: blocks a.b0 .. nblocks-1, the first of
+// them at bit a.start_bit
 template <int TYPE> cudaError_t launch_index_t(int dims, const DecodeArgs& a, uint16_t* lengths);
+
+// speculative segment-parallel rebuild (kernels.cuh spec_index_kernel), 1-3 D
+struct SpecIndexArgs {
+  const void* in;
+  uint64_t start_bit;    // first block of the stream
+  uint64_t avail_bits;   // end of the buffer the stream lies in
+  uint64_t seg_bits;     // segment t covers bits [start_bit + t * seg_bits, + seg_bits)
+  uint32_t nseg;
+  uint32_t margin_bits;  // a walk stops this far before avail_bits (worst-case block + a word)
+  Params prm;
+  uint64_t* exit;        // [nseg] where the walk of segment t left the segment = where segment t+1 is entered
+  uint32_t* cnt;         // [nseg] blocks between the entry and the exit of segment t
+  uint32_t* changed;     // pass 1: set when some exit moved
+  const uint64_t* off;   // [nseg] pass 2: number of the first block of segment t
+  uint16_t* lengths;     // pass 2
+  uint64_t nblocks;
+};
+template <int TYPE> cudaError_t launch_spec_index_t(int dims, int pass, const SpecIndexArgs& a, cudaStream_t st);
 
 }  // namespace zb
