@@ -373,6 +373,8 @@ def other_configs(torch, zb, dev, peak):
         elif len(shape) == 2:
             y, x = g[0][:, None], g[1][None, :]
             f = torch.sin(2 * np.pi * (3 * x + 0.5 * y)) + 0.25 * torch.sin(14 * np.pi * x * y)
+        elif len(shape) == 1:
+            f = torch.sin(40 * np.pi * g[0]) + 0.25 * torch.sin(300 * np.pi * g[0] ** 2)
         else:
             w, z, y, x = g[0][:, None, None, None], g[1][None, :, None, None], g[2][None, None, :, None], g[3][None, None, None, :]
             f = torch.sin(2 * np.pi * (x + 0.5 * y)) * torch.cos(3 * np.pi * z) + 0.25 * torch.sin(5 * np.pi * w * x)
@@ -384,6 +386,7 @@ def other_configs(torch, zb, dev, peak):
              ("3D fp32 1024^3 rate 8", (SIDE, SIDE, SIDE), torch.float32, {"rate": 8}),
              ("2D fp32 16384^2 rate 8", (16384, 16384), torch.float32, {"rate": 8}),
              ("4D fp64 64^4 rate 8", (64, 64, 64, 64), torch.float64, {"rate": 8}),
+             ("1D fp64 2^28 rate 8", (1 << 28,), torch.float64, {"rate": 8}),
              ("3D int32 1024^3 reversible", (SIDE, SIDE, SIDE), torch.int32, {"reversible": True})]
     out, cached = {}, (None, None, None)
     for name, shape, dtype, mode in cases:

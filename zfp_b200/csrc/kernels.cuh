@@ -595,8 +595,8 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   typename TR::Scalar v[N];
   uint32_t bits = 0;
   bool small = false;
-  if constexpr (N == 4) {
-    if (prm.maxbits <= 64) {  // the whole block in a register pair
+  if constexpr (N == 4 && OFFS == 0) {
+    if (prm.maxbits <= 64) {  // fixed rate, the whole block in a register pair (its maxbits bits are all its own)
       SmallReader br;
       br.init(in, bitpos, prm.maxbits);
       br.lut4 = lut4;
