@@ -252,6 +252,9 @@ encode_kernel(const typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Pa
 #ifndef ZB_SMALL8_F32
 #define ZB_SMALL8_F32 0  // the same steps for 3-D blocks of 32-bit values (experiment)
 #endif
+#ifndef ZB_ENC64_CTAS
+#define ZB_ENC64_CTAS 3  // CTAs of 128 threads per SM the lossy 64-bit encode kernels are compiled for (register cap 168)
+#endif
 #ifndef ZB_REV32_CTAS
 #define ZB_REV32_CTAS 6  // CTAs of 64 threads per SM the reversible 32-bit kernels are compiled for (register cap 170)
 #endif
@@ -272,7 +275,7 @@ template <int TYPE> struct EncCfg {
   __host__ __device__ static constexpr int min_ctas(bool rev)
   {
     // 64-bit: 384 threads per SM (<= 168 registers per thread), as with 6 CTAs of 64 threads
-    return Traits<TYPE>::P == 64 ? (rev ? 2 : 3) * 128 / threads : (rev ? ZB_REV32_CTAS : 9) * 64 / threads;
+    return Traits<TYPE>::P == 64 ? (rev ? 2 : ZB_ENC64_CTAS) * 128 / threads : (rev ? ZB_REV32_CTAS : 9) * 64 / threads;
   }
 };
 // the staged kernels' CTA shape: 2-D blocks of 32-bit values carry a 9-10 KB table per CTA (encode_planes_small8 /
