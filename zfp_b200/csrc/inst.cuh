@@ -256,7 +256,7 @@ cudaError_t run_decode(const DecodeArgs& a)
     if (a.staged && a.lengths)
       return run_decode_var<TYPE, DIMS, REV>(a);
   auto kernel = decode_kernel<TYPE, DIMS, OFFS, REV>;
-  constexpr size_t smem = plane_smem_bytes<TYPE, DIMS>() + (DIMS == 1 ? kDecLut4Bytes : 0);
+  constexpr size_t smem = DIMS == 1 ? (size_t)kDecLut4Bytes : plane_smem_bytes<TYPE, DIMS>();
   cudaError_t e = allow_smem(kernel, smem);
   if (e != cudaSuccess) return e;
   const uint64_t ctas = (a.b1 - a.b0 + kThreads - 1) / kThreads;

@@ -582,8 +582,9 @@ decode_kernel(typename Traits<TYPE>::Scalar* __restrict__ data, Geom g, Params p
   PW* sp = reinterpret_cast<PW*>(smem_raw) + (threadIdx.x >> 5) * (TR::P * 32) + (threadIdx.x & 31);
   uint32_t lut4 = 0;
   if constexpr (N == 4) {
-    // the decoder table of the 4-value blocks (kDecLut4), one copy per CTA behind the plane buffers
-    uint4* lut = reinterpret_cast<uint4*>(reinterpret_cast<PW*>(smem_raw) + (kThreads / 32) * (TR::P * 32));
+    // the decoder table of the 4-value blocks (kDecLut4), one copy per CTA; these blocks deposit their planes straight
+    // into the coefficients (decode_planes4_direct), so there is no plane buffer and sp is never dereferenced
+    uint4* lut = reinterpret_cast<uint4*>(smem_raw);
     for (int i = threadIdx.x; i < kDecLut4Bytes / 16; i += kThreads)
       lut[i] = __ldg(reinterpret_cast<const uint4*>(kDecLut4) + i);
     __syncthreads();
