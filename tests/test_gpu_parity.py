@@ -313,6 +313,17 @@ def test_foreign_stream_index_rebuilt_in_parallel(zb, port, monkeypatch):
         assert words.nbytes * 8 >= 1 << 23, "test case too small for the parallel rebuild"
         assert launches_par > launches_ser, "the parallel rebuild did not run"
         assert t_par < 0.6 * t_ser, (shape, mode, t_par, t_ser)
+    # a payload that starts in the middle of a word (something was written before it)
+    dtype, shape, mode = cases[1]
+    a = make_field(shape, dtype, seed=32, kind="smooth")
+    n4 = list(reversed(a.shape)) + [0] * (4 - a.ndim)
+    shifted = port.compress_raw(a.reshape(-1), 0, a.dtype, n4, None, mode, start_bit=77)[0]
+    want = port.decompress(port.compress(a, **mode), a.shape, a.dtype, **mode)
+    n0 = zb.launch_count()
+    got, _ = zb.decompress_numpy(shifted, a.shape, a.dtype, start_bit=77, index=None, **mode)
+    assert got.tobytes() == want.tobytes()
+    assert zb.launch_count() - n0 > 6, "the parallel rebuild did not run"
+
 
 
 def test_untrusted_block_index_cannot_mislead_the_decoder(zb, port):
