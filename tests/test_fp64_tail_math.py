@@ -94,3 +94,26 @@ def test_the_bound_is_needed():
     d = [float(v) for v in c]
     xform_inv(d, 3, inv_lift_f64)
     assert [int(f) for f in d] != a
+
+
+def test_lift_gain_is_the_largest_column_entry_of_what_the_lift_shifts_or_returns():
+    """gain() (= lift_gain in codec.cuh): per axis 1, 3/2, 1, 5/4 for the inputs x, y, z, w - derived here from the
+    lift itself: every value it shifts ("y + (w >> 1)") or returns, as a linear form of the four inputs."""
+    from fractions import Fraction as F
+    forms = []
+    x, y, z, w = ([F(int(i == j)) for j in range(4)] for i in range(4))
+    add = lambda a, b: [p + q for p, q in zip(a, b)]
+    sub = lambda a, b: [p - q for p, q in zip(a, b)]
+    half = lambda a: [p / 2 for p in a]
+    dbl = lambda a: [2 * p for p in a]
+    y = add(y, half(w)); forms.append(y)             # y += w >> 1     (shifted next)
+    w = sub(w, half(y))                              # w -= y >> 1
+    y = add(y, w); w = sub(dbl(w), y)
+    z = add(z, x); x = sub(dbl(x), z)
+    y = add(y, z); z = sub(dbl(z), y)
+    w = add(w, x); x = sub(dbl(x), w)
+    forms += [x, y, z, w]                            # returned: shifted by the next pass or converted at the end
+    col = [max(abs(f[j]) for f in forms) for j in range(4)]
+    assert col == [F(1), F(3, 2), F(1), F(5, 4)]
+    assert [gain(j, 1) for j in range(4)] == [float(c) for c in col]
+    assert gain(1 + 4 * 3 + 16 * 1, 3) == 1.5 * 1.25 * 1.5
