@@ -34,6 +34,12 @@
 
 namespace zb {
 
+// 64-bit 3-D decode: 1 = the CTA's warps rendezvous before the straight-line tail (shared instruction fetch).  It paid
+// while the tail was 1900 instructions of integer lifting; with the FP64-pipe tail (half as long) it does not any more
+// (1024^3 fp64 rate 4 / 8 / 16 decompress with: 3.90 / 4.94 / 6.00 ms, without: 3.73 / 4.94 / 5.92 ms)
+#ifndef ZB_DEC_TAIL_SYNC
+#define ZB_DEC_TAIL_SYNC 0
+#endif
 #ifndef ZB_FP64_TAIL
 #define ZB_FP64_TAIL 1  // inverse transform of fp64 blocks on the FP64 pipe where that is exact (decode_block)
 #endif
@@ -2200,7 +2206,7 @@ __device__ __forceinline__ uint32_t decode_block(typename Traits<TYPE>::Scalar (
       // the warps of the CTA (PS: of the warpgroup) enter the long straight-line tail together (shared instruction fetch)
       if constexpr (PS)
         wg_barrier();
-      else
+      else if constexpr (ZB_DEC_TAIL_SYNC || REV)  // (reversible mode keeps the long integer tail, and the rendezvous: 13.4 against 13.7 ms)
         __syncthreads();
     }
     else if constexpr (P == 64) {
